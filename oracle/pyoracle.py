@@ -1,0 +1,188 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes driver for the CPU oracle (oracle/gi_oracle.cpp). Imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import build as _build  # noqa: E402
+
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_bp = C.POINTER(C.c_byte)
+
+STATUS_NAMES = ["SUCCESS", "INCONSISTENT_INPUT", "NON_POS_HESSIAN", "INFEASIBLE", "MAX_ITER_REACHED",
+                "LINEAR_DEPENDENCY_DETECTED", "OVERCONSTRAINED_PROBLEM", "UNKNOWN"]
+INACTIVE, LOWER, UPPER, EQUALITY, LOWER_BOUND, UPPER_BOUND, FIXED = range(7)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_build.library_path())
+        _lib.gi_oracle_dot4.restype = C.c_double
+        _lib.gi_oracle_dot32.restype = C.c_double
+        _lib.gi_oracle_as_create.restype = C.c_void_p
+    return _lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _stride(a, per):
+    """element stride between instances: 0 when the array is shared (ndim one less)."""
+    return 0 if a is None or a.size == per else per
+
+
+def solve_batch(G, a, Cm, bl, bu, xl=None, xu=None, max_iter=500, big_bnd=1e100, nthreads=1,
+                want_L=False, instrument=False):
+    """G: [B,n,n] (each n x n block column-major, i.e. G[b, j, i] = G_b(i, j); symmetric input makes
+    this immaterial), a: [B,n], Cm: [B,mc,n] (row i = constraint normal i = column i of the reference's
+    n x mc column-major C), bl/bu: [B,mc], xl/xu: [B,n] or None. Arrays with one dimension less are
+    shared by all instances (stride 0). Returns a dict of numpy arrays.
+    """
+    G = _f64(G)
+    a = _f64(a)
+    Cm = _f64(Cm)
+    bl = _f64(bl)
+    bu = _f64(bu)
+    xl = _f64(xl)
+    xu = _f64(xu)
+    n = G.shape[-1]
+    mc = Cm.shape[-2] if Cm.size else 0
+    nb = n if xl is not None and xl.size else 0
+    m = mc + nb
+    Bs = [arr.shape[0] for arr, nd in ((G, 3), (a, 2), (Cm, 3), (bl, 2), (bu, 2)) if arr.ndim == nd]
+    if xl is not None and xl.ndim == 2:
+        Bs.append(xl.shape[0])
+    B = max(Bs) if Bs else 1
+    x = np.empty((B, n))
+    u = np.empty((B, m))
+    f = np.empty(B)
+    iters = np.empty(B, dtype=np.int32)
+    status = np.empty(B, dtype=np.int32)
+    act = np.empty((B, m), dtype=np.int8)
+    alist = np.empty((B, n), dtype=np.int32)
+    nact = np.empty(B, dtype=np.int32)
+    L = np.empty((B, n, n)) if want_L else None
+    flops = np.empty(B) if instrument else None
+    margin = np.empty(B) if instrument else None
+    if Cm.size == 0:
+        Cm = np.zeros((1,))
+        bl = np.zeros((1,))
+        bu = np.zeros((1,))
+    worst = lib().gi_oracle_solve_batch(
+        C.c_int(n), C.c_int(mc), C.c_int(nb), C.c_long(B),
+        _dp(G), C.c_long(_stride(G, n * n) if G.ndim == 3 else 0), C.c_int(n),
+        _dp(a), C.c_long(n if a.ndim == 2 else 0),
+        _dp(Cm), C.c_long(mc * n if Cm.ndim == 3 else 0), C.c_int(n),
+        _dp(bl), C.c_long(mc if bl.ndim == 2 else 0), _dp(bu), C.c_long(mc if bu.ndim == 2 else 0),
+        _dp(xl), C.c_long(n if (xl is not None and xl.ndim == 2) else 0),
+        _dp(xu), C.c_long(n if (xu is not None and xu.ndim == 2) else 0),
+        C.c_int(max_iter), C.c_double(big_bnd),
+        _dp(x), _dp(u), _dp(f), _ip(iters), _ip(status), act.ctypes.data_as(c_bp), _ip(alist), _ip(nact),
+        _dp(L), _dp(flops), _dp(margin), C.c_int(nthreads))
+    out = dict(x=x, u=u, f=f, iterations=iters, status=status, active_set=act, active_list=alist,
+               n_active=nact, worst=worst)
+    if want_L:
+        out["L"] = L
+    if instrument:
+        out["flops"] = flops
+        out["margin"] = margin
+    return out
+
+
+def solve_trace(G, a, Cm, bl, bu, xl=None, xu=None, max_iter=500, big_bnd=1e100, max_events=4096):
+    """Single QP, returns (result dict with 'events' [ne,7] = it,p,status,l,kind,t1,t2 and J, R)."""
+    G = _f64(G)
+    a = _f64(a)
+    Cm = _f64(Cm)
+    bl = _f64(bl)
+    bu = _f64(bu)
+    xl = _f64(xl)
+    xu = _f64(xu)
+    n = G.shape[-1]
+    mc = Cm.shape[0] if Cm.size else 0
+    nb = n if xl is not None and xl.size else 0
+    m = mc + nb
+    x = np.empty(n)
+    u = np.empty(m)
+    f = C.c_double()
+    it = C.c_int()
+    ne = C.c_int()
+    ev = np.zeros((max_events, 7))
+    J = np.empty((n, n))
+    R = np.empty((n, n))
+    if Cm.size == 0:
+        Cm = np.zeros((1,))
+        bl = np.zeros((1,))
+        bu = np.zeros((1,))
+    st = lib().gi_oracle_solve_trace(
+        C.c_int(n), C.c_int(mc), C.c_int(nb), _dp(G), C.c_int(n), _dp(a), _dp(Cm), C.c_int(n), _dp(bl), _dp(bu),
+        _dp(xl), _dp(xu), C.c_int(max_iter), C.c_double(big_bnd), _dp(x), _dp(u), C.byref(f), C.byref(it),
+        _dp(ev), C.c_int(max_events), C.byref(ne), _dp(J), _dp(R))
+    return dict(status=st, x=x, u=u, f=f.value, iterations=it.value, events=ev[:min(ne.value, max_events)],
+                J=J.T.copy(), R=R.T.copy())
+
+
+class ActiveSet:
+    """Handle on the oracle's ActiveSet restatement (src/internal/ActiveSet.cpp)."""
+
+    def __init__(self, n_cstr, n_bnd=0):
+        self.n = n_cstr + n_bnd
+        self.h = C.c_void_p(lib().gi_oracle_as_create(C.c_int(n_cstr), C.c_int(n_bnd)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().gi_oracle_as_destroy(self.h)
+            self.h = None
+
+    def activate(self, idx, status):
+        lib().gi_oracle_as_activate(self.h, C.c_int(idx), C.c_int(status))
+
+    def deactivate(self, active_idx):
+        lib().gi_oracle_as_deactivate(self.h, C.c_int(active_idx))
+
+    def reset(self):
+        lib().gi_oracle_as_reset(self.h)
+
+    def query(self):
+        st = np.zeros(self.n, dtype=np.int8)
+        al = np.zeros(max(self.n, 1), dtype=np.int32)
+        cnt = np.zeros(8, dtype=np.int32)
+        q = lib().gi_oracle_as_query(self.h, st.ctypes.data_as(c_bp), _ip(al), _ip(cnt))
+        return st.tolist(), al[:q].tolist(), cnt.tolist()
+
+
+def dot4(a, b):
+    a = _f64(a)
+    b = _f64(b)
+    return lib().gi_oracle_dot4(C.c_int(a.size), _dp(a), _dp(b))
+
+
+def dot32(a, b):
+    a = _f64(a)
+    b = _f64(b)
+    return lib().gi_oracle_dot32(C.c_int(a.size), _dp(a), _dp(b))
+
+
+def givens(p, q):
+    out = np.zeros(3)
+    lib().gi_oracle_givens(C.c_double(p), C.c_double(q), _dp(out))
+    return tuple(out)
