@@ -1,0 +1,189 @@
+/* jrlqp_b200.h — C-ABI of the B200-native batched Goldfarb-Idnani QP solver.
+ *
+ * Drop-in boundary for ONE path of jrl-umi3218/jrl-qp: GoldfarbIdnaniSolver::solve
+ * (include/jrl-qp/GoldfarbIdnaniSolver.h:27-33, src/GoldfarbIdnaniSolver.cpp:18-54) and the
+ * DualSolver accessors (include/jrl-qp/DualSolver.h:26-60), batched: every call solves `batch`
+ * independent strictly convex QPs
+ *
+ *      min 1/2 x^T G x + a^T x   s.t.  bl <= C^T x <= bu,  xl <= x <= xu
+ *
+ * with hand-written FP64 CUDA kernels for sm_100a. batch == 1 behaves like one call on the
+ * reference object. The reference has no FFI layer of its own (it is a C++ class library over
+ * Eigen::Ref views); the entry points below carry exactly what those views carry: a pointer, a
+ * leading dimension, and — because the call is batched — an element stride between instances
+ * (0 = the array is shared by all instances).
+ *
+ * There is no CPU fallback: every entry point fails with JRLQP_ERR_CUDA when no sm_100 device
+ * is usable.
+ *
+ * Plain C: pointers, sizes and PODs only (no torch / Eigen / STL types).
+ */
+#ifndef JRLQP_B200_H
+#define JRLQP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define JRLQP_B200_VERSION 100 /* 0.1.0 */
+
+/* include/jrl-qp/enums.h:14-23 — jrl::qp::ActivationStatus (same values, int8 storage) */
+enum jrlqp_activation_status
+{
+  JRLQP_INACTIVE = 0,
+  JRLQP_LOWER = 1,
+  JRLQP_UPPER = 2,
+  JRLQP_EQUALITY = 3,
+  JRLQP_LOWER_BOUND = 4,
+  JRLQP_UPPER_BOUND = 5,
+  JRLQP_FIXED = 6
+};
+
+/* include/jrl-qp/enums.h:26-37 — jrl::qp::TerminationStatus (same values) */
+enum jrlqp_termination_status
+{
+  JRLQP_SUCCESS = 0,
+  JRLQP_INCONSISTENT_INPUT = 1,
+  JRLQP_NON_POS_HESSIAN = 2,
+  JRLQP_INFEASIBLE = 3,
+  JRLQP_MAX_ITER_REACHED = 4,
+  JRLQP_LINEAR_DEPENDENCY_DETECTED = 5,
+  JRLQP_OVERCONSTRAINED_PROBLEM = 6,
+  JRLQP_UNKNOWN = 7
+};
+
+/* Library-level error codes (returned by the API functions; never stored in status arrays). */
+#define JRLQP_OK 0
+#define JRLQP_ERR_CUDA (-1) /* CUDA runtime/driver error, or no sm_100 device */
+#define JRLQP_ERR_ARG (-2) /* invalid argument (sizes, null pointer, unsupported n) */
+#define JRLQP_ERR_CAPACITY (-3) /* batch larger than the capacity given to jrlqp_create */
+
+/* include/jrl-qp/SolverOptions.h:14-22 — jrl::qp::SolverOptions. log_flags is carried for API
+ * parity only: the Matlab-syntax logger (include/jrl-qp/utils/Logger.h) is out of scope. */
+typedef struct jrlqp_options
+{
+  int32_t max_iter; /* maxIter_  = 500   */
+  double big_bnd; /* bigBnd_   = 1e100 */
+  int32_t warm_start; /* warmStart_ = false; honoured only by jrlqp_solve_batch_warm_* */
+  uint32_t log_flags; /* logFlags_ = 0     */
+} jrlqp_options;
+
+/* One batch of problems. All pointers live in the same memory space (device for *_device entry
+ * points, host for *_host). "stride" = distance in ELEMENTS between instance k and k+1; 0 shares
+ * the array. Matrices are column-major with a leading dimension, as Eigen::Ref<MatrixXd> views
+ * (include/jrl-qp/defs.h:11-14).
+ *   G  n x n, lower triangle read (src/GoldfarbIdnaniSolver.cpp:58). NOT overwritten: the factor
+ *      the reference leaves in G is returned through jrlqp_result.L when asked for.
+ *   C  n x mc, one constraint normal per column (include/jrl-qp/GoldfarbIdnaniSolver.h:22-26).
+ *   xl == NULL  <=>  no bounds (src/GoldfarbIdnaniSolver.cpp:28).
+ *   as_in: optional warm-start activation status, int8 x (mc+nb) per instance, general
+ *      constraints first (include/jrl-qp/experimental/GoldfarbIdnaniSolver.h:27-34).
+ */
+typedef struct jrlqp_problem
+{
+  int64_t batch;
+  const double * G;
+  int64_t G_stride;
+  int32_t ldg;
+  const double * a;
+  int64_t a_stride;
+  const double * C;
+  int64_t C_stride;
+  int32_t ldc;
+  const double * bl;
+  int64_t bl_stride;
+  const double * bu;
+  int64_t bu_stride;
+  const double * xl;
+  int64_t xl_stride;
+  const double * xu;
+  int64_t xu_stride;
+  const int8_t * as_in;
+  int64_t as_stride;
+} jrlqp_problem;
+
+/* Dense outputs, instance-major. Any pointer may be NULL (that output is skipped) except x.
+ *   x           [batch][n]        DualSolver::solution()       src/DualSolver.cpp:33-36
+ *   u           [batch][mc+nb]    DualSolver::multipliers()    src/DualSolver.cpp:38-69 (signed,
+ *                                 + for UPPER/UPPER_BOUND, - otherwise; constraints then bounds)
+ *   f           [batch]           DualSolver::objectiveValue() src/DualSolver.cpp:71-74
+ *   iterations  [batch]           DualSolver::iterations()     src/DualSolver.cpp:76-79
+ *   status      [batch]           return value of solve()      (jrlqp_termination_status)
+ *   active_set  [batch][mc+nb]    DualSolver::activeSet()      (jrlqp_activation_status, int8)
+ *   active_list [batch][n]        ordered active list (ActiveSet::operator[]), -1 padded
+ *   n_active    [batch]           ActiveSet::nbActiveCstr()
+ *   L           [batch][n][n]     column-major, ld n: lower triangle = Cholesky factor that the
+ *                                 reference leaves in G (strict upper triangle not written)
+ * On JRLQP_NON_POS_HESSIAN x, u, f are zero and the active set is empty (the reference leaves
+ * them unspecified).
+ */
+typedef struct jrlqp_result
+{
+  double * x;
+  double * u;
+  double * f;
+  int32_t * iterations;
+  int32_t * status;
+  int8_t * active_set;
+  int32_t * active_list;
+  int32_t * n_active;
+  double * L;
+} jrlqp_result;
+
+typedef struct jrlqp_solver jrlqp_solver;
+
+/* GoldfarbIdnaniSolver(nbVar, nbCstr, useBounds) (include/jrl-qp/GoldfarbIdnaniSolver.h:17-19)
+ * + DualSolver::resize. batch_capacity bounds the batch of the *_host entry points (device staging
+ * buffers are allocated once here, honouring the reference's no-allocation-in-solve contract,
+ * tests/GoldfarbIdnaniSolverTest.cpp:113-117). device = CUDA ordinal. n <= 128. */
+int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds, int64_t batch_capacity, int32_t device);
+int jrlqp_destroy(jrlqp_solver * s);
+
+/* DualSolver::options(const SolverOptions&) (src/DualSolver.cpp:26-31) */
+void jrlqp_default_options(jrlqp_options * opt);
+int jrlqp_set_options(jrlqp_solver * s, const jrlqp_options * opt);
+int jrlqp_get_options(const jrlqp_solver * s, jrlqp_options * opt);
+
+/* GoldfarbIdnaniSolver::solve (src/GoldfarbIdnaniSolver.cpp:18-54), batched, DEVICE pointers,
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ * Returns JRLQP_OK once enqueued; per-instance statuses land in res->status. */
+int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream);
+
+/* Same call with HOST pointers: host->device copies, the kernels, device->host copies, then a
+ * synchronise. Host memory may be pageable or pinned. Returns the worst jrlqp_termination_status
+ * of the batch (>= 0) or a negative JRLQP_ERR_*. */
+int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res);
+
+/* Introspection used by the benchmark harness. */
+typedef struct jrlqp_kernel_info
+{
+  int32_t threads_per_qp; /* 32: one QP per warp */
+  int32_t rows_per_thread;
+  int32_t smem_bytes_per_qp;
+  int32_t qps_per_sm; /* resident CTAs per SM */
+  int32_t grid; /* persistent CTAs */
+  int32_t num_sms;
+  int32_t stage_c; /* 1: constraint matrix staged in shared memory */
+  int32_t regs_per_thread;
+} jrlqp_kernel_info;
+int jrlqp_get_kernel_info(const jrlqp_solver * s, jrlqp_kernel_info * info);
+/* Tuning knob: 0 = C read from global/L2, 1 = staged in shared memory, -1 = automatic. */
+int jrlqp_set_stage_c(jrlqp_solver * s, int32_t mode);
+/* Number of kernels this library has launched since it was loaded (all solvers). */
+int64_t jrlqp_launch_count(void);
+/* Last CUDA error string seen by this solver ("" if none). */
+const char * jrlqp_last_error(const jrlqp_solver * s);
+int jrlqp_version(void);
+
+/* FP64 roofline probe: runs a dependent-free DFMA loop on every SM and returns the measured
+ * TFLOP/s (2 flops per FMA), or a negative error. Used by bench.py for the roofline denominator. */
+double jrlqp_measure_fp64_tflops(int32_t device, int32_t repeats);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* JRLQP_B200_H */

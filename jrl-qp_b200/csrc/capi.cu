@@ -1,0 +1,516 @@
+// Host side of the C-ABI (include/jrlqp_b200.h): solver handle, shared-memory layout, kernel
+// dispatch, and the host-pointer entry point that pipelines H2D copies, the persistent kernel and
+// D2H copies over a few streams. Pure CUDA runtime — no PyTorch, no CPU fallback.
+#include "gi_dense_warp.cuh"
+#include "jrlqp_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace jrlqp;
+
+namespace
+{
+
+std::atomic<long long> g_launches{0};
+
+constexpr int kStreams = 3;
+constexpr int kMaxChunks = 64;
+
+using KernelFn = void (*)(const GiParams);
+
+KernelFn pick_kernel(int rpt, bool stage)
+{
+  switch(rpt)
+  {
+    case 1:
+      return stage ? gi_dense_warp_kernel<1, true> : gi_dense_warp_kernel<1, false>;
+    case 2:
+      return stage ? gi_dense_warp_kernel<2, true> : gi_dense_warp_kernel<2, false>;
+    case 3:
+      return stage ? gi_dense_warp_kernel<3, true> : gi_dense_warp_kernel<3, false>;
+    case 4:
+      return stage ? gi_dense_warp_kernel<4, true> : gi_dense_warp_kernel<4, false>;
+    default:
+      return nullptr;
+  }
+}
+
+struct Layout
+{
+  int ldj, ldcs, npad;
+  int off_R, off_x, off_z, off_d, off_r, off_u, off_C, off_alist, off_stat;
+  int total_doubles;
+};
+
+Layout make_layout(int n, int mc, int nb, int rpt, bool stage)
+{
+  Layout L{};
+  L.ldj = n | 1;
+  L.ldcs = n | 1;
+  L.npad = 32 * rpt;
+  int o = n * L.ldj;
+  L.off_R = o;
+  o += n * (n + 1) / 2;
+  L.off_x = o;
+  o += L.npad;
+  L.off_z = o;
+  o += L.npad;
+  L.off_d = o;
+  o += L.npad;
+  L.off_r = o;
+  o += L.npad;
+  L.off_u = o;
+  o += L.npad + 32;
+  L.off_C = o;
+  o += stage ? mc * L.ldcs : 0;
+  L.off_alist = o;
+  o += (n + 1) / 2 + 1;
+  L.off_stat = o;
+  o += (mc + nb + 7) / 8 + 1;
+  L.total_doubles = o;
+  return L;
+}
+
+} // namespace
+
+struct jrlqp_solver
+{
+  int n = 0, mc = 0, nb = 0, m = 0;
+  long long capacity = 0;
+  int device = 0;
+  jrlqp_options opt{};
+  int rpt = 1;
+  int stage_mode = -1; // -1 auto
+  bool stage = false;
+  Layout lay{};
+  KernelFn kernel = nullptr;
+  int smem_bytes = 0;
+  int occ = 0;
+  int num_sms = 0;
+  int regs = 0;
+  int max_smem_optin = 0;
+  // device-side scratch
+  unsigned long long * d_counters = nullptr; // kMaxChunks counters
+  int next_counter = 0;
+  // staging for the host entry point
+  double *d_G = nullptr, *d_a = nullptr, *d_C = nullptr, *d_bl = nullptr, *d_bu = nullptr, *d_xl = nullptr, *d_xu = nullptr;
+  double *d_x = nullptr, *d_u = nullptr, *d_f = nullptr, *d_L = nullptr;
+  int *d_it = nullptr, *d_status = nullptr, *d_alist = nullptr, *d_nact = nullptr;
+  signed char * d_act = nullptr;
+  bool staging_ready = false;
+  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+  std::string err;
+
+  bool check(cudaError_t e, const char * what)
+  {
+    if(e == cudaSuccess) return true;
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+  }
+};
+
+#define CK(call)                             \
+  do                                         \
+  {                                          \
+    if(!s->check((call), #call)) return JRLQP_ERR_CUDA; \
+  } while(0)
+
+static int configure_kernel(jrlqp_solver * s)
+{
+  // choose staging of C: automatic mode stages it when that costs no residency
+  auto try_cfg = [&](bool stage, int & occ, int & smem, KernelFn & fn, Layout & lay) -> int
+  {
+    lay = make_layout(s->n, s->mc, s->nb, s->rpt, stage);
+    smem = lay.total_doubles * 8;
+    fn = pick_kernel(s->rpt, stage);
+    occ = 0;
+    if(smem > s->max_smem_optin) return 0;
+    if(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return 0;
+    }
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smem) != cudaSuccess)
+    {
+      cudaGetLastError();
+      occ = 0;
+    }
+    return occ;
+  };
+  int occN = 0, occS = 0, smN = 0, smS = 0;
+  KernelFn fnN = nullptr, fnS = nullptr;
+  Layout layN{}, layS{};
+  try_cfg(false, occN, smN, fnN, layN);
+  if(s->mc > 0) try_cfg(true, occS, smS, fnS, layS);
+  bool stage;
+  if(s->stage_mode == 0)
+    stage = false;
+  else if(s->stage_mode == 1)
+    stage = occS > 0;
+  else
+    stage = occS > 0 && occS >= occN; // automatic: stage only when residency is not reduced
+  if(stage)
+  {
+    s->occ = occS;
+    s->smem_bytes = smS;
+    s->kernel = fnS;
+    s->lay = layS;
+  }
+  else
+  {
+    s->occ = occN;
+    s->smem_bytes = smN;
+    s->kernel = fnN;
+    s->lay = layN;
+  }
+  s->stage = stage;
+  if(s->occ <= 0)
+  {
+    s->err = "problem does not fit in shared memory (n too large for the dense warp kernel)";
+    return JRLQP_ERR_ARG;
+  }
+  cudaFuncAttributes attr;
+  CK(cudaFuncGetAttributes(&attr, s->kernel));
+  s->regs = attr.numRegs;
+  return JRLQP_OK;
+}
+
+extern "C"
+{
+
+int jrlqp_version(void)
+{
+  return JRLQP_B200_VERSION;
+}
+
+void jrlqp_default_options(jrlqp_options * opt)
+{
+  opt->max_iter = 500;
+  opt->big_bnd = 1e100;
+  opt->warm_start = 0;
+  opt->log_flags = 0;
+}
+
+int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds, int64_t batch_capacity, int32_t device)
+{
+  if(!out) return JRLQP_ERR_ARG;
+  *out = nullptr;
+  if(n < 1 || n > 128 || mc < 0 || batch_capacity < 0) return JRLQP_ERR_ARG;
+  jrlqp_solver * s = new jrlqp_solver();
+  s->n = n;
+  s->mc = mc;
+  s->nb = use_bounds ? n : 0;
+  s->m = mc + s->nb;
+  s->capacity = batch_capacity;
+  s->device = device;
+  s->rpt = (n + 31) / 32;
+  jrlqp_default_options(&s->opt);
+  *out = s; // returned even on CUDA failure so that jrlqp_last_error is readable
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if(device < 0 || device >= ndev)
+  {
+    s->err = "no such CUDA device";
+    return JRLQP_ERR_CUDA;
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if(prop.major != 10)
+  {
+    s->err = "this library contains sm_100a code only (Blackwell B200 required)";
+    return JRLQP_ERR_CUDA;
+  }
+  s->num_sms = prop.multiProcessorCount;
+  s->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  int rc = configure_kernel(s);
+  if(rc != JRLQP_OK) return rc;
+  CK(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kMaxChunks));
+  CK(cudaMemset(s->d_counters, 0, sizeof(unsigned long long) * kMaxChunks));
+  for(int i = 0; i < kStreams; ++i) CK(cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking));
+  return JRLQP_OK;
+}
+
+int jrlqp_destroy(jrlqp_solver * s)
+{
+  if(!s) return JRLQP_OK;
+  cudaSetDevice(s->device);
+  void * ptrs[] = {s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+                   s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
+  for(void * p : ptrs)
+    if(p) cudaFree(p);
+  for(int i = 0; i < kStreams; ++i)
+    if(s->streams[i]) cudaStreamDestroy(s->streams[i]);
+  delete s;
+  return JRLQP_OK;
+}
+
+int jrlqp_set_options(jrlqp_solver * s, const jrlqp_options * opt)
+{
+  if(!s || !opt) return JRLQP_ERR_ARG;
+  s->opt = *opt;
+  return JRLQP_OK;
+}
+
+int jrlqp_get_options(const jrlqp_solver * s, jrlqp_options * opt)
+{
+  if(!s || !opt) return JRLQP_ERR_ARG;
+  *opt = s->opt;
+  return JRLQP_OK;
+}
+
+int jrlqp_set_stage_c(jrlqp_solver * s, int32_t mode)
+{
+  if(!s || mode < -1 || mode > 1) return JRLQP_ERR_ARG;
+  s->stage_mode = mode;
+  cudaSetDevice(s->device);
+  return configure_kernel(s);
+}
+
+int jrlqp_get_kernel_info(const jrlqp_solver * s, jrlqp_kernel_info * info)
+{
+  if(!s || !info) return JRLQP_ERR_ARG;
+  info->threads_per_qp = 32;
+  info->rows_per_thread = s->rpt;
+  info->smem_bytes_per_qp = s->smem_bytes;
+  info->qps_per_sm = s->occ;
+  info->grid = s->occ * s->num_sms;
+  info->num_sms = s->num_sms;
+  info->stage_c = s->stage ? 1 : 0;
+  info->regs_per_thread = s->regs;
+  return JRLQP_OK;
+}
+
+int64_t jrlqp_launch_count(void)
+{
+  return g_launches.load();
+}
+
+const char * jrlqp_last_error(const jrlqp_solver * s)
+{
+  return s ? s->err.c_str() : "null solver";
+}
+
+static int validate(const jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res)
+{
+  if(!s || !pb || !res) return JRLQP_ERR_ARG;
+  if(pb->batch < 0) return JRLQP_ERR_ARG;
+  if(!pb->G || !pb->a || !res->x) return JRLQP_ERR_ARG;
+  if(pb->ldg < s->n) return JRLQP_ERR_ARG;
+  if(s->mc > 0 && (!pb->C || !pb->bl || !pb->bu || pb->ldc < s->n)) return JRLQP_ERR_ARG;
+  if(s->nb > 0 && (!pb->xl || !pb->xu)) return JRLQP_ERR_ARG;
+  if(s->nb == 0 && (pb->xl || pb->xu)) return JRLQP_ERR_ARG; // bounds given to a solver built without them
+  return JRLQP_OK;
+}
+
+static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter)
+{
+  GiParams p{};
+  p.n = s->n;
+  p.mc = s->mc;
+  p.nb = s->nb;
+  p.ldg = pb->ldg;
+  p.ldc = s->mc ? pb->ldc : s->n;
+  p.batch = pb->batch;
+  p.max_iter = s->opt.max_iter;
+  p.big_bnd = s->opt.big_bnd;
+  p.G = pb->G;
+  p.sG = pb->G_stride;
+  p.a = pb->a;
+  p.sa = pb->a_stride;
+  p.C = pb->C;
+  p.sC = pb->C_stride;
+  p.bl = pb->bl;
+  p.sbl = pb->bl_stride;
+  p.bu = pb->bu;
+  p.sbu = pb->bu_stride;
+  p.xl = pb->xl;
+  p.sxl = pb->xl_stride;
+  p.xu = pb->xu;
+  p.sxu = pb->xu_stride;
+  p.x = res->x;
+  p.u = res->u;
+  p.f = res->f;
+  p.iterations = res->iterations;
+  p.status = res->status;
+  p.active_set = res->active_set;
+  p.active_list = res->active_list;
+  p.n_active = res->n_active;
+  p.L = res->L;
+  p.counter = counter;
+  p.ldj = s->lay.ldj;
+  p.ldcs = s->lay.ldcs;
+  p.npad = s->lay.npad;
+  p.off_R = s->lay.off_R;
+  p.off_x = s->lay.off_x;
+  p.off_z = s->lay.off_z;
+  p.off_d = s->lay.off_d;
+  p.off_r = s->lay.off_r;
+  p.off_u = s->lay.off_u;
+  p.off_C = s->lay.off_C;
+  p.off_alist = s->lay.off_alist;
+  p.off_stat = s->lay.off_stat;
+  long long grid = std::min<long long>((long long)s->occ * s->num_sms, std::max<long long>(pb->batch, 1));
+  CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  s->kernel<<<(unsigned)grid, 32, s->smem_bytes, st>>>(p);
+  g_launches.fetch_add(1);
+  CK(cudaGetLastError());
+  return JRLQP_OK;
+}
+
+int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream)
+{
+  int rc = validate(s, pb, res);
+  if(rc != JRLQP_OK) return rc;
+  if(pb->batch == 0) return JRLQP_OK;
+  CK(cudaSetDevice(s->device));
+  unsigned long long * counter = s->d_counters + (s->next_counter++ % kMaxChunks);
+  return launch(s, pb, res, (cudaStream_t)stream, counter);
+}
+
+static int ensure_staging(jrlqp_solver * s, bool wantL)
+{
+  const long long B = std::max<long long>(s->capacity, 1);
+  const long long n = s->n, mc = s->mc, m = s->m;
+  if(!s->staging_ready)
+  {
+    CK(cudaMalloc(&s->d_G, sizeof(double) * B * n * n));
+    CK(cudaMalloc(&s->d_a, sizeof(double) * B * n));
+    if(mc)
+    {
+      CK(cudaMalloc(&s->d_C, sizeof(double) * B * mc * n));
+      CK(cudaMalloc(&s->d_bl, sizeof(double) * B * mc));
+      CK(cudaMalloc(&s->d_bu, sizeof(double) * B * mc));
+    }
+    if(s->nb)
+    {
+      CK(cudaMalloc(&s->d_xl, sizeof(double) * B * n));
+      CK(cudaMalloc(&s->d_xu, sizeof(double) * B * n));
+    }
+    CK(cudaMalloc(&s->d_x, sizeof(double) * B * n));
+    CK(cudaMalloc(&s->d_u, sizeof(double) * B * std::max<long long>(m, 1)));
+    CK(cudaMalloc(&s->d_f, sizeof(double) * B));
+    CK(cudaMalloc(&s->d_it, sizeof(int) * B));
+    CK(cudaMalloc(&s->d_status, sizeof(int) * B));
+    CK(cudaMalloc(&s->d_alist, sizeof(int) * B * n));
+    CK(cudaMalloc(&s->d_nact, sizeof(int) * B));
+    CK(cudaMalloc(&s->d_act, std::max<long long>(B * m, 1)));
+    s->staging_ready = true;
+  }
+  if(wantL && !s->d_L) CK(cudaMalloc(&s->d_L, sizeof(double) * B * n * n));
+  return JRLQP_OK;
+}
+
+// Copy `count` instances of a (possibly strided, possibly ld-padded) host array into the dense
+// device staging buffer. rows x cols column-major blocks with leading dimension ld.
+static cudaError_t h2d(double * dst, const double * src, long long stride, long long count, int rows, int cols, int ld, cudaStream_t st)
+{
+  const long long blk = (long long)rows * cols;
+  if(stride == 0) count = 1;
+  if(ld == rows && (stride == blk || count == 1)) return cudaMemcpyAsync(dst, src, sizeof(double) * blk * count, cudaMemcpyHostToDevice, st);
+  if(ld == rows) return cudaMemcpy2DAsync(dst, sizeof(double) * blk, src, sizeof(double) * stride, sizeof(double) * blk, count, cudaMemcpyHostToDevice, st);
+  for(long long k = 0; k < count; ++k)
+  {
+    cudaError_t e = cudaMemcpy2DAsync(dst + k * blk, sizeof(double) * rows, src + k * stride, sizeof(double) * ld, sizeof(double) * rows, cols,
+                                      cudaMemcpyHostToDevice, st);
+    if(e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res)
+{
+  int rc = validate(s, pb, res);
+  if(rc != JRLQP_OK) return rc;
+  if(pb->batch > s->capacity) return JRLQP_ERR_CAPACITY;
+  if(pb->batch == 0) return JRLQP_SUCCESS;
+  CK(cudaSetDevice(s->device));
+  rc = ensure_staging(s, res->L != nullptr);
+  if(rc != JRLQP_OK) return rc;
+
+  const long long B = pb->batch;
+  const long long n = s->n, mc = s->mc, m = s->m;
+  // Pipeline: split the batch into chunks; chunk c runs H2D -> kernel -> D2H on stream c % kStreams,
+  // so the copy engines and the SMs overlap across chunks.
+  const long long per_qp_bytes = 8 * (n * n + n + mc * n + 2 * mc + 2 * s->nb);
+  long long chunk = std::max<long long>((long long)s->occ * s->num_sms * 4, (48ll << 20) / std::max<long long>(per_qp_bytes, 1));
+  long long nchunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (B + chunk - 1) / chunk));
+  chunk = (B + nchunks - 1) / nchunks;
+
+  for(long long c = 0; c < nchunks; ++c)
+  {
+    const long long b0 = c * chunk;
+    const long long cnt = std::min(chunk, B - b0);
+    if(cnt <= 0) break;
+    cudaStream_t st = s->streams[c % kStreams];
+    jrlqp_problem dp{};
+    dp.batch = cnt;
+    // shared (stride 0) arrays are uploaded by every chunk into slot b0 (tiny, keeps chunks independent)
+    auto up = [&](double * dbase, const double * h, long long hstride, int rows, int cols, int ld, const double *& dptr, int64_t & dstride) -> cudaError_t
+    {
+      const long long blk = (long long)rows * cols;
+      double * d = dbase + b0 * blk;
+      dptr = d;
+      dstride = hstride == 0 ? 0 : blk;
+      return h2d(d, h + b0 * hstride, hstride, cnt, rows, cols, ld, st);
+    };
+    CK(up(s->d_G, pb->G, pb->G_stride, (int)n, (int)n, pb->ldg, dp.G, dp.G_stride));
+    dp.ldg = (int)n;
+    CK(up(s->d_a, pb->a, pb->a_stride, (int)n, 1, (int)n, dp.a, dp.a_stride));
+    if(mc)
+    {
+      CK(up(s->d_C, pb->C, pb->C_stride, (int)n, (int)mc, pb->ldc, dp.C, dp.C_stride));
+      CK(up(s->d_bl, pb->bl, pb->bl_stride, (int)mc, 1, (int)mc, dp.bl, dp.bl_stride));
+      CK(up(s->d_bu, pb->bu, pb->bu_stride, (int)mc, 1, (int)mc, dp.bu, dp.bu_stride));
+    }
+    dp.ldc = (int)n;
+    if(s->nb)
+    {
+      CK(up(s->d_xl, pb->xl, pb->xl_stride, (int)n, 1, (int)n, dp.xl, dp.xl_stride));
+      CK(up(s->d_xu, pb->xu, pb->xu_stride, (int)n, 1, (int)n, dp.xu, dp.xu_stride));
+    }
+    jrlqp_result dr{};
+    dr.x = s->d_x + b0 * n;
+    dr.u = res->u ? s->d_u + b0 * m : nullptr;
+    dr.f = res->f ? s->d_f + b0 : nullptr;
+    dr.iterations = res->iterations ? s->d_it + b0 : nullptr;
+    dr.status = s->d_status + b0;
+    dr.active_set = res->active_set ? s->d_act + b0 * m : nullptr;
+    dr.active_list = res->active_list ? s->d_alist + b0 * n : nullptr;
+    dr.n_active = res->n_active ? s->d_nact + b0 : nullptr;
+    dr.L = res->L ? s->d_L + b0 * n * n : nullptr;
+    rc = launch(s, &dp, &dr, st, s->d_counters + (c % kMaxChunks));
+    if(rc != JRLQP_OK) return rc;
+    CK(cudaMemcpyAsync(res->x + b0 * n, dr.x, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, st));
+    if(res->u && m) CK(cudaMemcpyAsync(res->u + b0 * m, dr.u, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, st));
+    if(res->f) CK(cudaMemcpyAsync(res->f + b0, dr.f, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    if(res->iterations) CK(cudaMemcpyAsync(res->iterations + b0, dr.iterations, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st));
+    if(res->status) CK(cudaMemcpyAsync(res->status + b0, dr.status, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st));
+    if(res->active_set && m) CK(cudaMemcpyAsync(res->active_set + b0 * m, dr.active_set, cnt * m, cudaMemcpyDeviceToHost, st));
+    if(res->active_list) CK(cudaMemcpyAsync(res->active_list + b0 * n, dr.active_list, sizeof(int) * cnt * n, cudaMemcpyDeviceToHost, st));
+    if(res->n_active) CK(cudaMemcpyAsync(res->n_active + b0, dr.n_active, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st));
+    if(res->L) CK(cudaMemcpyAsync(res->L + b0 * n * n, dr.L, sizeof(double) * cnt * n * n, cudaMemcpyDeviceToHost, st));
+  }
+  for(int i = 0; i < kStreams; ++i) CK(cudaStreamSynchronize(s->streams[i]));
+
+  // worst status of the batch (the reference's return value, reduced over the batch)
+  int worst = 0;
+  if(res->status)
+  {
+    for(long long b = 0; b < B; ++b) worst = std::max(worst, res->status[b]);
+  }
+  else
+  {
+    std::vector<int> hs((size_t)B);
+    CK(cudaMemcpy(hs.data(), s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    for(long long b = 0; b < B; ++b) worst = std::max(worst, hs[(size_t)b]);
+  }
+  return worst;
+}
+
+} // extern "C"

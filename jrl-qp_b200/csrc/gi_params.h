@@ -1,0 +1,74 @@
+// Kernel parameter block shared by the host API (capi.cu) and the device code.
+#pragma once
+#include <stdint.h>
+
+namespace jrlqp
+{
+
+// jrl::qp::ActivationStatus / TerminationStatus values (include/jrl-qp/enums.h:14-37)
+enum : int
+{
+  ST_INACTIVE = 0,
+  ST_LOWER = 1,
+  ST_UPPER = 2,
+  ST_EQUALITY = 3,
+  ST_LOWER_BOUND = 4,
+  ST_UPPER_BOUND = 5,
+  ST_FIXED = 6
+};
+enum : int
+{
+  TS_SUCCESS = 0,
+  TS_INCONSISTENT_INPUT = 1,
+  TS_NON_POS_HESSIAN = 2,
+  TS_INFEASIBLE = 3,
+  TS_MAX_ITER_REACHED = 4,
+  TS_LINEAR_DEPENDENCY_DETECTED = 5,
+  TS_OVERCONSTRAINED_PROBLEM = 6,
+  TS_UNKNOWN = 7
+};
+
+struct GiParams
+{
+  // sizes
+  int n, mc, nb;
+  int ldg, ldc;
+  long long batch;
+  // options
+  int max_iter;
+  double big_bnd;
+  // inputs (device pointers, element strides between instances; 0 = shared)
+  const double * G;
+  long long sG;
+  const double * a;
+  long long sa;
+  const double * C;
+  long long sC;
+  const double * bl;
+  long long sbl;
+  const double * bu;
+  long long sbu;
+  const double * xl;
+  long long sxl;
+  const double * xu;
+  long long sxu;
+  // outputs (device pointers, dense; nullable except x)
+  double * x;
+  double * u;
+  double * f;
+  int * iterations;
+  int * status;
+  signed char * active_set;
+  int * active_list;
+  int * n_active;
+  double * L;
+  // persistent work queue
+  unsigned long long * counter;
+  // shared-memory layout (computed on the host, in doubles unless noted)
+  int ldj; // leading dimension of the row-major J/L buffer (odd => conflict-free row-strided access)
+  int ldcs; // leading dimension of the staged C (odd), if staged
+  int npad; // 32 * rows_per_thread
+  int off_R, off_x, off_z, off_d, off_r, off_u, off_C, off_alist, off_stat; // offsets in doubles
+};
+
+} // namespace jrlqp

@@ -1,0 +1,340 @@
+"""Python mirror of the reference's solver interface over the C-ABI (include/jrlqp_b200.h).
+
+`GoldfarbIdnaniSolver` keeps the reference's method names and argument meaning
+(include/jrl-qp/GoldfarbIdnaniSolver.h:15-33, include/jrl-qp/DualSolver.h:26-60):
+solve(G, a, C, bl, bu, xl, xu) -> TerminationStatus, solution(), multipliers(), objectiveValue(),
+iterations(), activeSet(), resetActiveSet(), options(), resize(). `BatchedGoldfarbIdnaniSolver` is the
+same call over a batch. Both go through ctypes to libjrlqp_b200.so — there is no CPU fallback: if the
+CUDA library is missing or no B200 is visible, construction raises.
+"""
+import ctypes as C
+import enum
+import os
+
+import numpy as np
+
+from . import build as _build
+
+
+class ActivationStatus(enum.IntEnum):  # include/jrl-qp/enums.h:14-23
+    INACTIVE = 0
+    LOWER = 1
+    UPPER = 2
+    EQUALITY = 3
+    LOWER_BOUND = 4
+    UPPER_BOUND = 5
+    FIXED = 6
+
+
+class TerminationStatus(enum.IntEnum):  # include/jrl-qp/enums.h:26-37
+    SUCCESS = 0
+    INCONSISTENT_INPUT = 1
+    NON_POS_HESSIAN = 2
+    INFEASIBLE = 3
+    MAX_ITER_REACHED = 4
+    LINEAR_DEPENDENCY_DETECTED = 5
+    OVERCONSTRAINED_PROBLEM = 6
+    UNKNOWN = 7
+
+
+class SolverOptions:
+    """include/jrl-qp/SolverOptions.h:14-88 (chained setters; log stream not carried)."""
+
+    def __init__(self):
+        self.maxIter_ = 500
+        self.bigBnd_ = 1e100
+        self.warmStart_ = False
+        self.logFlags_ = 0
+
+    def maxIter(self, v=None):
+        if v is None:
+            return self.maxIter_
+        self.maxIter_ = int(v)
+        return self
+
+    def bigBnd(self, v=None):
+        if v is None:
+            return self.bigBnd_
+        self.bigBnd_ = float(v)
+        return self
+
+    def warmStart(self, v=None):
+        if v is None:
+            return self.warmStart_
+        self.warmStart_ = bool(v)
+        return self
+
+    def logFlags(self, v=None):
+        if v is None:
+            return self.logFlags_
+        self.logFlags_ = int(v)
+        return self
+
+
+class _Options(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("big_bnd", C.c_double), ("warm_start", C.c_int32), ("log_flags", C.c_uint32)]
+
+
+class _Problem(C.Structure):
+    _fields_ = [("batch", C.c_int64),
+                ("G", C.c_void_p), ("G_stride", C.c_int64), ("ldg", C.c_int32),
+                ("a", C.c_void_p), ("a_stride", C.c_int64),
+                ("C", C.c_void_p), ("C_stride", C.c_int64), ("ldc", C.c_int32),
+                ("bl", C.c_void_p), ("bl_stride", C.c_int64),
+                ("bu", C.c_void_p), ("bu_stride", C.c_int64),
+                ("xl", C.c_void_p), ("xl_stride", C.c_int64),
+                ("xu", C.c_void_p), ("xu_stride", C.c_int64),
+                ("as_in", C.c_void_p), ("as_stride", C.c_int64)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("u", C.c_void_p), ("f", C.c_void_p), ("iterations", C.c_void_p),
+                ("status", C.c_void_p), ("active_set", C.c_void_p), ("active_list", C.c_void_p),
+                ("n_active", C.c_void_p), ("L", C.c_void_p)]
+
+
+class KernelInfo(C.Structure):
+    _fields_ = [("threads_per_qp", C.c_int32), ("rows_per_thread", C.c_int32), ("smem_bytes_per_qp", C.c_int32),
+                ("qps_per_sm", C.c_int32), ("grid", C.c_int32), ("num_sms", C.c_int32), ("stage_c", C.c_int32),
+                ("regs_per_thread", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTED_SYMBOLS = [
+    "jrlqp_version", "jrlqp_default_options", "jrlqp_create", "jrlqp_destroy", "jrlqp_set_options",
+    "jrlqp_get_options", "jrlqp_solve_batch_device", "jrlqp_solve_batch_host", "jrlqp_get_kernel_info",
+    "jrlqp_set_stage_c", "jrlqp_launch_count", "jrlqp_last_error", "jrlqp_measure_fp64_tflops",
+]
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libjrlqp_b200.so")
+
+
+def load_library():
+    """Load libjrlqp_b200.so (building it in-tree if it is missing). Raises if that fails."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            _build.build_cuda()
+        lib = C.CDLL(path)
+        lib.jrlqp_launch_count.restype = C.c_int64
+        lib.jrlqp_last_error.restype = C.c_char_p
+        lib.jrlqp_last_error.argtypes = [C.c_void_p]
+        lib.jrlqp_measure_fp64_tflops.restype = C.c_double
+        lib.jrlqp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32]
+        lib.jrlqp_destroy.argtypes = [C.c_void_p]
+        lib.jrlqp_set_options.argtypes = [C.c_void_p, C.POINTER(_Options)]
+        lib.jrlqp_get_kernel_info.argtypes = [C.c_void_p, C.POINTER(KernelInfo)]
+        lib.jrlqp_set_stage_c.argtypes = [C.c_void_p, C.c_int32]
+        lib.jrlqp_solve_batch_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
+        lib.jrlqp_solve_batch_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
+        _lib = lib
+    return _lib
+
+
+def launch_count():
+    return int(load_library().jrlqp_launch_count())
+
+
+def measure_fp64_tflops(device=0, repeats=5):
+    return float(load_library().jrlqp_measure_fp64_tflops(C.c_int32(device), C.c_int32(repeats)))
+
+
+class JrlQpError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor (host pinned or device)
+
+
+class BatchedGoldfarbIdnaniSolver:
+    """Batched GoldfarbIdnaniSolver. Arrays follow the C-ABI layout:
+    G [B,n,n] column-major blocks, a [B,n], C [B,mc,n] (row i = normal of constraint i, which IS the
+    reference's n x mc column-major matrix), bl/bu [B,mc], xl/xu [B,n] or None. An array with one
+    dimension less is shared by the whole batch (stride 0)."""
+
+    def __init__(self, nbVar, nbCstr, useBounds, batch_capacity=1, device=0):
+        self._lib = load_library()
+        self.n, self.mc, self.nb = int(nbVar), int(nbCstr), (int(nbVar) if useBounds else 0)
+        self.m = self.mc + self.nb
+        self.capacity = int(batch_capacity)
+        self.device = device
+        self._h = C.c_void_p()
+        rc = self._lib.jrlqp_create(C.byref(self._h), self.n, self.mc, int(bool(useBounds)), self.capacity, device)
+        if rc != 0:
+            msg = self._lib.jrlqp_last_error(self._h).decode() if self._h else "allocation failed"
+            if self._h:
+                self._lib.jrlqp_destroy(self._h)
+                self._h = None
+            raise JrlQpError(f"jrlqp_create failed ({rc}): {msg}")
+        self._options = SolverOptions()
+        self.last = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.jrlqp_destroy(h)
+            self._h = None
+
+    # DualSolver::options
+    def options(self, opt=None):
+        if opt is None:
+            return self._options
+        self._options = opt
+        o = _Options(opt.maxIter_, opt.bigBnd_, int(opt.warmStart_), opt.logFlags_)
+        rc = self._lib.jrlqp_set_options(self._h, C.byref(o))
+        if rc != 0:
+            raise JrlQpError("jrlqp_set_options failed")
+        return self
+
+    def kernel_info(self):
+        info = KernelInfo()
+        self._lib.jrlqp_get_kernel_info(self._h, C.byref(info))
+        return info.as_dict()
+
+    def set_stage_c(self, mode):
+        rc = self._lib.jrlqp_set_stage_c(self._h, int(mode))
+        if rc != 0:
+            raise JrlQpError(f"jrlqp_set_stage_c failed: {self._lib.jrlqp_last_error(self._h).decode()}")
+
+    def _problem(self, B, G, a, Cm, bl, bu, xl, xu, shared, ldg=None, ldc=None):
+        n, mc = self.n, self.mc
+        st = lambda name, per: 0 if name in shared else per
+        pb = _Problem()
+        pb.batch = B
+        pb.G, pb.G_stride, pb.ldg = _ptr(G), st("G", n * n), ldg or n
+        pb.a, pb.a_stride = _ptr(a), st("a", n)
+        pb.C, pb.C_stride, pb.ldc = _ptr(Cm), st("C", mc * n), ldc or n
+        pb.bl, pb.bl_stride = _ptr(bl), st("bl", mc)
+        pb.bu, pb.bu_stride = _ptr(bu), st("bu", mc)
+        pb.xl, pb.xl_stride = _ptr(xl), st("xl", n)
+        pb.xu, pb.xu_stride = _ptr(xu), st("xu", n)
+        pb.as_in, pb.as_stride = None, 0
+        return pb
+
+    def solve(self, G, a, Cm, bl, bu, xl=None, xu=None, want_L=False, want_active_list=True):
+        """HOST arrays (numpy). Returns the worst TerminationStatus; results in self.last (dict)."""
+        f64 = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        G, a, Cm, bl, bu, xl, xu = map(f64, (G, a, Cm, bl, bu, xl, xu))
+        if self.nb == 0:
+            xl = xu = None
+        n, mc, m = self.n, self.mc, self.m
+        full = {"G": 3, "a": 2, "C": 3, "bl": 2, "bu": 2, "xl": 2, "xu": 2}
+        arrs = {"G": G, "a": a, "C": Cm, "bl": bl, "bu": bu, "xl": xl, "xu": xu}
+        shared = {k for k, v in arrs.items() if v is not None and v.ndim < full[k]}
+        Bs = [v.shape[0] for k, v in arrs.items() if v is not None and k not in shared]
+        B = max(Bs) if Bs else 1
+        if mc == 0:
+            Cm = bl = bu = None
+        x = np.empty((B, n))
+        u = np.empty((B, m))
+        f = np.empty(B)
+        it = np.empty(B, dtype=np.int32)
+        status = np.empty(B, dtype=np.int32)
+        act = np.empty((B, m), dtype=np.int8)
+        alist = np.empty((B, n), dtype=np.int32) if want_active_list else None
+        nact = np.empty(B, dtype=np.int32)
+        L = np.zeros((B, n, n)) if want_L else None
+        pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, shared)
+        res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(it), _ptr(status), _ptr(act), _ptr(alist), _ptr(nact), _ptr(L))
+        rc = self._lib.jrlqp_solve_batch_host(self._h, C.byref(pb), C.byref(res))
+        if rc < 0:
+            raise JrlQpError(f"jrlqp_solve_batch_host failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
+        self.last = dict(x=x, u=u, f=f, iterations=it, status=status, active_set=act, active_list=alist,
+                         n_active=nact, worst=rc)
+        if want_L:
+            self.last["L"] = L
+        return TerminationStatus(rc)
+
+    def solve_device(self, B, G, a, Cm, bl, bu, xl, xu, x, u=None, f=None, iterations=None, status=None,
+                     active_set=None, active_list=None, n_active=None, L=None, stream=0, shared=()):
+        """DEVICE pointers (ints or torch CUDA tensors); asynchronous on `stream` (cudaStream_t as int)."""
+        pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, set(shared))
+        res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(iterations), _ptr(status), _ptr(active_set),
+                      _ptr(active_list), _ptr(n_active), _ptr(L))
+        rc = self._lib.jrlqp_solve_batch_device(self._h, C.byref(pb), C.byref(res), C.c_void_p(stream))
+        if rc != 0:
+            raise JrlQpError(f"jrlqp_solve_batch_device failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
+
+
+class GoldfarbIdnaniSolver:
+    """One-QP-per-call mirror of jrl::qp::GoldfarbIdnaniSolver (batch of 1 through the same kernels).
+
+    G is n x n (symmetric, lower triangle read); C is n x nbCstr with one constraint per COLUMN, as
+    in the reference (tests pass `qpp.C.transpose()`, tests/GoldfarbIdnaniSolverTest.cpp:89).
+    After solve(), G's lower triangle holds the Cholesky factor, as with the reference.
+    """
+
+    def __init__(self, nbVar=0, nbCstr=0, useBounds=False, device=0):
+        self._device = device
+        self._impl = None
+        self._opt = SolverOptions()
+        self._res = None
+        if nbVar > 0:
+            self.resize(nbVar, nbCstr, useBounds)
+
+    def resize(self, nbVar, nbCstr, useBounds):
+        if self._impl is None or (self._impl.n, self._impl.mc, self._impl.nb > 0) != (nbVar, nbCstr, bool(useBounds)):
+            self._impl = BatchedGoldfarbIdnaniSolver(nbVar, nbCstr, useBounds, 1, self._device)
+            self._impl.options(self._opt)
+
+    def options(self, opt=None):
+        if opt is None:
+            return self._opt
+        self._opt = opt
+        if self._impl is not None:
+            self._impl.options(opt)
+        return self
+
+    def solve(self, G, a, Cmat, bl, bu, xl, xu):
+        G = np.asarray(G)
+        n = G.shape[0]
+        Cmat = np.asarray(Cmat, dtype=np.float64).reshape(n, -1)
+        nbCstr = Cmat.shape[1]
+        useBnd = xl is not None and np.size(xl) > 0
+        self.resize(n, nbCstr, useBnd)
+        # column-major n x mc  ==  row-major [mc, n]
+        Cm = np.ascontiguousarray(Cmat.T)
+        Gc = np.ascontiguousarray(np.asarray(G, dtype=np.float64).T)  # column-major blocks
+        st = self._impl.solve(Gc[None], np.asarray(a, dtype=np.float64)[None], Cm[None] if nbCstr else None,
+                              np.asarray(bl, dtype=np.float64)[None] if nbCstr else None,
+                              np.asarray(bu, dtype=np.float64)[None] if nbCstr else None,
+                              np.asarray(xl, dtype=np.float64)[None] if useBnd else None,
+                              np.asarray(xu, dtype=np.float64)[None] if useBnd else None, want_L=True)
+        self._res = self._impl.last
+        if st != TerminationStatus.NON_POS_HESSIAN and isinstance(G, np.ndarray) and G.dtype == np.float64 and G.flags.writeable:
+            Lf = self._res["L"][0].T  # back to (i, j) indexing
+            il = np.tril_indices(n)
+            G[il] = Lf[il]  # G is an in/out argument in the reference (src/GoldfarbIdnaniSolver.cpp:58)
+        return st
+
+    def solution(self):
+        return self._res["x"][0]
+
+    def multipliers(self):
+        return self._res["u"][0]
+
+    def objectiveValue(self):
+        return float(self._res["f"][0])
+
+    def iterations(self):
+        return int(self._res["iterations"][0])
+
+    def activeSet(self):
+        return [ActivationStatus(int(v)) for v in self._res["active_set"][0]]
+
+    def resetActiveSet(self):
+        pass  # the stable solver resets its active set at every solve (src/GoldfarbIdnaniSolver.cpp:75)
