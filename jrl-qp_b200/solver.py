@@ -260,9 +260,13 @@ class BatchedGoldfarbIdnaniSolver:
         return TerminationStatus(rc)
 
     def solve_device(self, B, G, a, Cm, bl, bu, xl, xu, x, u=None, f=None, iterations=None, status=None,
-                     active_set=None, active_list=None, n_active=None, L=None, stream=0, shared=()):
-        """DEVICE pointers (ints or torch CUDA tensors); asynchronous on `stream` (cudaStream_t as int)."""
-        pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, set(shared))
+                     active_set=None, active_list=None, n_active=None, L=None, stream=0, shared=(), ldg=None, ldc=None,
+                     strides=None):
+        """DEVICE pointers (ints or torch CUDA tensors); asynchronous on `stream` (cudaStream_t as int).
+        `shared` names arrays with stride 0; `strides` overrides element strides, e.g. {"G": n * ldg}."""
+        pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, set(shared), ldg, ldc)
+        for k, v in (strides or {}).items():
+            setattr(pb, k + "_stride", int(v))
         res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(iterations), _ptr(status), _ptr(active_set),
                       _ptr(active_list), _ptr(n_active), _ptr(L))
         rc = self._lib.jrlqp_solve_batch_device(self._h, C.byref(pb), C.byref(res), C.c_void_p(stream))

@@ -87,6 +87,24 @@ int gi_oracle_solve_batch(int n,
         int st = solver.solve(Gs.data(), n, a + b * sa, C + b * sC, ldc, bl + b * sbl, bu + b * sbu, nb ? xl + b * sxl : nullptr,
                               nb ? xu + b * sxu : nullptr);
         localWorst = std::max(localWorst, st);
+        if(st == NON_POS_HESSIAN)
+        {
+          // The reference leaves x/u/f/active set unspecified (stale) when the factorisation fails
+          // (src/DualSolver.cpp:93-94); both the oracle and the CUDA path report zeros / empty set.
+          if(x) std::memset(x + b * n, 0, sizeof(double) * n);
+          if(u) std::memset(u + b * m, 0, sizeof(double) * m);
+          if(f) f[b] = 0;
+          if(iters) iters[b] = 0;
+          if(status) status[b] = st;
+          if(act) std::memset(act + b * m, 0, static_cast<size_t>(m));
+          if(active_list)
+            for(int k = 0; k < n; ++k) active_list[b * n + k] = -1;
+          if(nactive) nactive[b] = 0;
+          if(L_out) std::memcpy(L_out + b * static_cast<long>(n) * n, Gs.data(), sizeof(double) * n * n);
+          if(flops) flops[b] = solver.flops();
+          if(margin) margin[b] = solver.minMargin();
+          continue;
+        }
         if(x) std::memcpy(x + b * n, solver.solution(), sizeof(double) * n);
         if(u) std::memcpy(u + b * m, solver.multipliers(), sizeof(double) * m);
         if(f) f[b] = solver.objectiveValue();
