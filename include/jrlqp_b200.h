@@ -160,7 +160,7 @@ int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrl
 /* Introspection used by the benchmark harness. */
 typedef struct jrlqp_kernel_info
 {
-  int32_t threads_per_qp; /* 32: one QP per warp */
+  int32_t threads_per_qp; /* 32 * warps: one QP per CTA */
   int32_t rows_per_thread;
   int32_t smem_bytes_per_qp;
   int32_t qps_per_sm; /* resident CTAs per SM */

@@ -1,7 +1,7 @@
 // Host side of the C-ABI (include/jrlqp_b200.h): solver handle, shared-memory layout, kernel
 // dispatch, and the host-pointer entry point that pipelines H2D copies, the persistent kernel and
 // D2H copies over a few streams. Pure CUDA runtime — no PyTorch, no CPU fallback.
-#include "gi_dense_warp.cuh"
+#include "gi_dense_cta.cuh"
 #include "jrlqp_b200.h"
 
 #include <algorithm>
@@ -23,18 +23,18 @@ constexpr int kMaxChunks = 64;
 
 using KernelFn = void (*)(const GiParams);
 
-KernelFn pick_kernel(int rpt, bool stage)
+KernelFn pick_kernel(int warps, bool stage)
 {
-  switch(rpt)
+  switch(warps)
   {
     case 1:
-      return stage ? gi_dense_warp_kernel<1, true> : gi_dense_warp_kernel<1, false>;
+      return stage ? gi_dense_cta_kernel<1, true> : gi_dense_cta_kernel<1, false>;
     case 2:
-      return stage ? gi_dense_warp_kernel<2, true> : gi_dense_warp_kernel<2, false>;
+      return stage ? gi_dense_cta_kernel<2, true> : gi_dense_cta_kernel<2, false>;
     case 3:
-      return stage ? gi_dense_warp_kernel<3, true> : gi_dense_warp_kernel<3, false>;
+      return stage ? gi_dense_cta_kernel<3, true> : gi_dense_cta_kernel<3, false>;
     case 4:
-      return stage ? gi_dense_warp_kernel<4, true> : gi_dense_warp_kernel<4, false>;
+      return stage ? gi_dense_cta_kernel<4, true> : gi_dense_cta_kernel<4, false>;
     default:
       return nullptr;
   }
@@ -43,33 +43,49 @@ KernelFn pick_kernel(int rpt, bool stage)
 struct Layout
 {
   int ldj, ldcs, npad;
-  int off_R, off_x, off_z, off_d, off_r, off_u, off_C, off_alist, off_stat;
+  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_ldiag, off_scr, off_C;
+  int off_alist, off_gk, off_iscr, off_stat;
   int total_doubles;
 };
 
-Layout make_layout(int n, int mc, int nb, int rpt, bool stage)
+Layout make_layout(int n, int mc, int nb, int warps, bool stage)
 {
   Layout L{};
   L.ldj = n | 1;
   L.ldcs = n | 1;
-  L.npad = 32 * rpt;
+  L.npad = 32 * warps;
+  const int np = L.npad;
   int o = n * L.ldj;
   L.off_R = o;
   o += n * (n + 1) / 2;
   L.off_x = o;
-  o += L.npad;
+  o += np;
   L.off_z = o;
-  o += L.npad;
+  o += np;
   L.off_d = o;
-  o += L.npad;
+  o += np;
   L.off_r = o;
-  o += L.npad;
+  o += np;
   L.off_u = o;
-  o += L.npad + 32;
+  o += np + 2;
+  L.off_cv = o;
+  o += np;
+  L.off_gc = o;
+  o += np;
+  L.off_gs = o;
+  o += np;
+  L.off_ldiag = o;
+  o += np;
+  L.off_scr = o;
+  o += 16;
   L.off_C = o;
   o += stage ? mc * L.ldcs : 0;
   L.off_alist = o;
-  o += (n + 1) / 2 + 1;
+  o += np / 2 + 1;
+  L.off_gk = o;
+  o += np / 2 + 1;
+  L.off_iscr = o;
+  o += 8;
   L.off_stat = o;
   o += (mc + nb + 7) / 8 + 1;
   L.total_doubles = o;
@@ -84,7 +100,7 @@ struct jrlqp_solver
   long long capacity = 0;
   int device = 0;
   jrlqp_options opt{};
-  int rpt = 1;
+  int warps = 1;
   int stage_mode = -1; // -1 auto
   bool stage = false;
   Layout lay{};
@@ -125,9 +141,9 @@ static int configure_kernel(jrlqp_solver * s)
   // choose staging of C: automatic mode stages it when that costs no residency
   auto try_cfg = [&](bool stage, int & occ, int & smem, KernelFn & fn, Layout & lay) -> int
   {
-    lay = make_layout(s->n, s->mc, s->nb, s->rpt, stage);
+    lay = make_layout(s->n, s->mc, s->nb, s->warps, stage);
     smem = lay.total_doubles * 8;
-    fn = pick_kernel(s->rpt, stage);
+    fn = pick_kernel(s->warps, stage);
     occ = 0;
     if(smem > s->max_smem_optin) return 0;
     if(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -135,7 +151,7 @@ static int configure_kernel(jrlqp_solver * s)
       cudaGetLastError();
       return 0;
     }
-    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smem) != cudaSuccess)
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * s->warps, smem) != cudaSuccess)
     {
       cudaGetLastError();
       occ = 0;
@@ -208,7 +224,7 @@ int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds,
   s->m = mc + s->nb;
   s->capacity = batch_capacity;
   s->device = device;
-  s->rpt = (n + 31) / 32;
+  s->warps = (n + 31) / 32;
   jrlqp_default_options(&s->opt);
   *out = s; // returned even on CUDA failure so that jrlqp_last_error is readable
   int ndev = 0;
@@ -275,8 +291,8 @@ int jrlqp_set_stage_c(jrlqp_solver * s, int32_t mode)
 int jrlqp_get_kernel_info(const jrlqp_solver * s, jrlqp_kernel_info * info)
 {
   if(!s || !info) return JRLQP_ERR_ARG;
-  info->threads_per_qp = 32;
-  info->rows_per_thread = s->rpt;
+  info->threads_per_qp = 32 * s->warps;
+  info->rows_per_thread = 1;
   info->smem_bytes_per_qp = s->smem_bytes;
   info->qps_per_sm = s->occ;
   info->grid = s->occ * s->num_sms;
@@ -352,12 +368,19 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.off_d = s->lay.off_d;
   p.off_r = s->lay.off_r;
   p.off_u = s->lay.off_u;
+  p.off_cv = s->lay.off_cv;
+  p.off_gc = s->lay.off_gc;
+  p.off_gs = s->lay.off_gs;
+  p.off_ldiag = s->lay.off_ldiag;
+  p.off_scr = s->lay.off_scr;
   p.off_C = s->lay.off_C;
   p.off_alist = s->lay.off_alist;
+  p.off_gk = s->lay.off_gk;
+  p.off_iscr = s->lay.off_iscr;
   p.off_stat = s->lay.off_stat;
   long long grid = std::min<long long>((long long)s->occ * s->num_sms, std::max<long long>(pb->batch, 1));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-  s->kernel<<<(unsigned)grid, 32, s->smem_bytes, st>>>(p);
+  s->kernel<<<(unsigned)grid, 32 * s->warps, s->smem_bytes, st>>>(p);
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return JRLQP_OK;

@@ -1,0 +1,1125 @@
+// Dense cold-start Goldfarb-Idnani solver: ONE QP PER CTA of W warps (T = 32 W >= n threads, one
+// row / column per thread), persistent work-queue kernel, sm_100a.
+//
+// Replaces, for a batch of independent QPs, the reference path
+//   GoldfarbIdnaniSolver::solve -> DualSolver::solve -> {init_, selectViolatedConstraint_,
+//   computeStep_, computeStepLength_, addConstraint_, removeConstraint_}
+//   (src/GoldfarbIdnaniSolver.cpp:18-338, src/DualSolver.cpp:38-244, src/internal/ActiveSet.cpp).
+//
+// Why this shape (profiles/r01a_*): the algorithm is a chain of short BLAS-2 steps glued by two
+// strictly serial scalar recurrences per iteration — the back substitution r = R^-1 d1 (one FP64
+// division per link) and the Givens sweep of addConstraint_ (division + square root per link). A
+// single warp per QP spends ~8 cycles per instruction on those chains. Here
+//   * every BLAS-2 phase is spread over all T threads (thread = row, column or constraint),
+//   * the two recurrences, which are independent of each other, run CONCURRENTLY on different
+//     warps: warp 0 does the back substitution while warp 1 runs the Givens recurrence
+//     speculatively (its rotations are only applied if the step turns out to be a full step),
+//   * the Givens recurrence keeps only what is truly serial (t, u, rho); the second division and
+//     the products giving (c, s) are done lane-parallel afterwards, and the rotations are applied
+//     to J by all threads from the (c, s) table.
+//
+// Layout (per-QP state lives in the CTA's shared memory for the whole solve; HBM traffic is the
+// compulsory input read + output write only):
+//   Jb   n x ldj row-major, ldj odd: lower triangle of G -> L (in place) -> J = L^-T in the upper
+//        triangle, lower cleared. Row-major + odd ld makes both access patterns conflict-free:
+//        threads over columns (d = J^T n+) and threads over rows (z = J2 d2, column rotations).
+//   Rp   packed upper-triangular R, column k at k(k+1)/2.
+//   xs, zs, ds, rs, us, cv (selected normal), gc/gs (Givens table), ldiag, alist, stat, scratch.
+//   Cs   optional staged copy of C (mc x ldcs, ldcs odd, one normal per row).
+// Every floating-point result is produced in the canonical order that oracle/gi_oracle.cpp documents
+// (dot4 / dot32 / fma axpy / Eigen makeGivens): results are bit-identical to the oracle whatever W.
+#pragma once
+
+#include "gi_params.h"
+
+#include <cuda_runtime.h>
+
+namespace jrlqp
+{
+
+#define JRLQP_FULL 0xffffffffu
+#define JRLQP_NONE 0x7fffffff
+
+__device__ __forceinline__ double warp_sum32(double acc)
+{
+  // dot32 butterfly: acc[l] += acc[l ^ off], off = 16,8,4,2,1 (addition commutes => all lanes agree)
+#pragma unroll
+  for(int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(JRLQP_FULL, acc, off);
+  return acc;
+}
+
+template<int S>
+__device__ __forceinline__ double pick(const double (&v)[S], int slot)
+{
+  double r = v[0];
+#pragma unroll
+  for(int s = 1; s < S; ++s)
+    if(slot == s) r = v[s];
+  return r;
+}
+
+// Eigen JacobiRotation::makeGivens (real case); same operation order as the oracle.
+__device__ __forceinline__ void make_givens(double p, double q, double & c, double & s, double & r)
+{
+  if(q == 0.0)
+  {
+    c = p < 0.0 ? -1.0 : 1.0;
+    s = 0.0;
+    r = fabs(p);
+  }
+  else if(p == 0.0)
+  {
+    c = 0.0;
+    s = q < 0.0 ? 1.0 : -1.0;
+    r = fabs(q);
+  }
+  else if(fabs(p) > fabs(q))
+  {
+    double t = q / p;
+    double u = sqrt(fma(t, t, 1.0));
+    if(p < 0.0) u = -u;
+    c = 1.0 / u;
+    s = -t * c;
+    r = p * u;
+  }
+  else
+  {
+    double t = p / q;
+    double u = sqrt(fma(t, t, 1.0));
+    if(q < 0.0) u = -u;
+    s = -1.0 / u;
+    c = -t * s;
+    r = q * u;
+  }
+}
+
+// dot4 of two unit-stride vectors, evaluated redundantly by every calling thread (uniform result).
+__device__ __noinline__ double dot4_uniform(int len, const double * __restrict__ a, const double * __restrict__ b)
+{
+  double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  int k = 0;
+#pragma unroll 1
+  for(; k + 3 < len; k += 4)
+  {
+    c0 = fma(a[k], b[k], c0);
+    c1 = fma(a[k + 1], b[k + 1], c1);
+    c2 = fma(a[k + 2], b[k + 2], c2);
+    c3 = fma(a[k + 3], b[k + 3], c3);
+  }
+  if(k < len) c0 = fma(a[k], b[k], c0);
+  if(k + 1 < len) c1 = fma(a[k + 1], b[k + 1], c1);
+  if(k + 2 < len) c2 = fma(a[k + 2], b[k + 2], c2);
+  return (c0 + c1) + (c2 + c3);
+}
+
+struct Sel
+{
+  int p;
+  int st;
+};
+
+// Exact sequential restatement of selectViolatedConstraint_ (src/GoldfarbIdnaniSolver.cpp:84-134),
+// every thread redundantly. Only used when some constraint has BOTH slacks negative (bl > bu), the
+// one situation where the parallel "first minimum" differs from the reference's else-if chain.
+__device__ __noinline__ Sel select_sequential(int n,
+                                              int mc,
+                                              int nb,
+                                              const double * Cbase,
+                                              long long ldC,
+                                              const double * xs,
+                                              const double * bl,
+                                              const double * bu,
+                                              const double * xl,
+                                              const double * xu,
+                                              const signed char * stat)
+{
+  double smin = 0;
+  Sel sel{-1, ST_INACTIVE};
+  for(int i = 0; i < mc; ++i)
+  {
+    if(stat[i] == ST_INACTIVE)
+    {
+      double cx = dot4_uniform(n, Cbase + (long long)i * ldC, xs);
+      double sl = cx - bl[i];
+      if(sl < smin)
+      {
+        smin = sl;
+        sel = {i, ST_LOWER};
+      }
+      else
+      {
+        double su = bu[i] - cx;
+        if(su < smin)
+        {
+          smin = su;
+          sel = {i, ST_UPPER};
+        }
+      }
+    }
+  }
+  for(int i = 0; i < nb; ++i)
+  {
+    if(stat[mc + i] == ST_INACTIVE)
+    {
+      double sl = xs[i] - xl[i];
+      if(sl < smin)
+      {
+        smin = sl;
+        sel = {mc + i, ST_LOWER_BOUND};
+      }
+      else
+      {
+        double su = xu[i] - xs[i];
+        if(su < smin)
+        {
+          smin = su;
+          sel = {mc + i, ST_UPPER_BOUND};
+        }
+      }
+    }
+  }
+  return sel;
+}
+
+template<int W, bool STAGE_C>
+struct GiCta
+{
+  static constexpr int T = 32 * W;
+  // ---- immutable per-launch
+  const GiParams & P;
+  const int tid, lane, warp;
+  const int n, mc, nb, m, ldj;
+  double *Jb, *Rp, *xs, *zs, *ds, *rs, *us, *cv, *gc, *gs, *ldiag, *Cs, *scr;
+  int * alist;
+  int * gk;
+  int * iscr;
+  signed char * stat;
+  // ---- per-problem views
+  const double *Cb, *bl, *bu, *xl, *xu;
+  long long ldC; // leading dimension of the constraint-normal storage Cb (staged or global)
+  // ---- solver state (uniform across threads)
+  int q;
+  double f;
+
+  __device__ GiCta(const GiParams & p, double * smem)
+  : P(p), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), n(p.n), mc(p.mc), nb(p.nb), m(p.mc + p.nb), ldj(p.ldj)
+  {
+    Jb = smem;
+    Rp = smem + p.off_R;
+    xs = smem + p.off_x;
+    zs = smem + p.off_z;
+    ds = smem + p.off_d;
+    rs = smem + p.off_r;
+    us = smem + p.off_u;
+    cv = smem + p.off_cv;
+    gc = smem + p.off_gc;
+    gs = smem + p.off_gs;
+    ldiag = smem + p.off_ldiag;
+    scr = smem + p.off_scr;
+    Cs = smem + p.off_C;
+    alist = reinterpret_cast<int *>(smem + p.off_alist);
+    gk = reinterpret_cast<int *>(smem + p.off_gk);
+    iscr = reinterpret_cast<int *>(smem + p.off_iscr);
+    stat = reinterpret_cast<signed char *>(smem + p.off_stat);
+  }
+
+  __device__ __forceinline__ void sync() const
+  {
+    if(W == 1)
+      __syncwarp();
+    else
+      __syncthreads();
+  }
+  __device__ __forceinline__ static int colR(int k) { return (k * (k + 1)) >> 1; }
+
+  // ------------------------------------------------------------------------------------------
+  // init_ (src/GoldfarbIdnaniSolver.cpp:56-82): Cholesky, J = L^-T, x = -G^-1 a, f = a.x/2
+  // ------------------------------------------------------------------------------------------
+  __device__ bool init(long long b)
+  {
+    const double * __restrict__ Gb = P.G + b * P.sG;
+    const double * __restrict__ ab = P.a + b * P.sa;
+    const int ldg = P.ldg;
+    const int i = tid; // this thread's row (and, later, column)
+    const int ic = min(i, n - 1);
+
+    // stage the lower triangle of G (column-major in HBM: threads run down a column => coalesced)
+#pragma unroll 4
+    for(int j = 0; j < n; ++j)
+      if(i < n && i >= j) Jb[i * ldj + j] = __ldg(Gb + i + (long long)j * ldg);
+    if(STAGE_C)
+    {
+      // C is n x mc column-major: column c (one normal) is contiguous => coalesced along k
+      const double * __restrict__ Cg = P.C + b * P.sC;
+#pragma unroll 4
+      for(int c = 0; c < mc; ++c)
+        if(i < n) Cs[c * P.ldcs + i] = __ldg(Cg + i + (long long)c * P.ldc);
+    }
+    else if(mc > 0)
+    {
+      // pull this problem's C towards L2 while the factorisation runs (it is first needed by the scan)
+      const char * Cg = reinterpret_cast<const char *>(P.C + b * P.sC);
+      const long long bytes = ((long long)(mc - 1) * P.ldc + n) * 8;
+      for(long long o = (long long)tid * 128; o < bytes; o += (long long)T * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg + o));
+    }
+    sync();
+
+    // --- left-looking Cholesky, thread = row
+    {
+      const double * Li = Jb + ic * ldj;
+#pragma unroll 1
+      for(int k = 0; k < n; ++k)
+      {
+        double v = 0.0;
+        if(32 * warp + 31 >= k) // warps entirely above the pivot row have nothing to do
+        {
+          const double * Lk = Jb + k * ldj;
+          double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+          int j = 0;
+#pragma unroll 1
+          for(; j + 3 < k; j += 4)
+          {
+            a0 = fma(Li[j], Lk[j], a0);
+            a1 = fma(Li[j + 1], Lk[j + 1], a1);
+            a2 = fma(Li[j + 2], Lk[j + 2], a2);
+            a3 = fma(Li[j + 3], Lk[j + 3], a3);
+          }
+          if(j < k) a0 = fma(Li[j], Lk[j], a0);
+          if(j + 1 < k) a1 = fma(Li[j + 1], Lk[j + 1], a1);
+          if(j + 2 < k) a2 = fma(Li[j + 2], Lk[j + 2], a2);
+          v = Li[k] - ((a0 + a1) + (a2 + a3));
+          if(i == k) scr[0] = v;
+        }
+        sync();
+        double vk = scr[0];
+        if(vk <= 0.0) return false; // Eigen llt: "if (x <= 0) return k" -> NON_POS_HESSIAN (uniform)
+        double lkk = sqrt(vk);
+        if(i == k)
+        {
+          Jb[i * ldj + k] = lkk;
+          ldiag[k] = lkk;
+          rs[k] = 1.0 / lkk; // reciprocal of the diagonal for J = L^-T
+        }
+        else if(i > k && i < n)
+          Jb[i * ldj + k] = v / lkk;
+        sync();
+      }
+    }
+
+    // optional copy-out of L (what the reference leaves in G)
+    if(P.L != nullptr)
+    {
+      double * Lout = P.L + b * (long long)n * n;
+      for(int j = 0; j < n; ++j)
+        if(i < n && i >= j) Lout[i + (long long)j * n] = Jb[i * ldj + j];
+    }
+
+    // --- x = -G^-1 a on warp 0 (serial division chain, rows over the lanes, W slots), while the
+    //     other warps already build their columns of J = L^-T; warp 0 joins afterwards.
+    if(warp == 0)
+    {
+      double y[W];
+#pragma unroll
+      for(int s = 0; s < W; ++s) y[s] = lane + 32 * s < n ? __ldg(ab + lane + 32 * s) : 0.0;
+#pragma unroll 1
+      for(int k = 0; k < n; ++k)
+      {
+        double yk = __shfl_sync(JRLQP_FULL, pick<W>(y, k >> 5), k & 31) / ldiag[k];
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          int r = lane + 32 * s;
+          if(r == k)
+            y[s] = yk;
+          else if(r > k && r < n)
+            y[s] = fma(-yk, Jb[r * ldj + k], y[s]);
+        }
+      }
+#pragma unroll 1
+      for(int k = n - 1; k >= 0; --k)
+      {
+        double xk = __shfl_sync(JRLQP_FULL, pick<W>(y, k >> 5), k & 31) / ldiag[k];
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          int r = lane + 32 * s;
+          if(r == k)
+            y[s] = xk;
+          else if(r < k)
+            y[s] = fma(-xk, Jb[k * ldj + r], y[s]);
+        }
+      }
+      double facc = 0.0;
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        int r = lane + 32 * s;
+        if(r < n)
+        {
+          double xi = -y[s];
+          xs[r] = xi;
+          facc = fma(__ldg(ab + r), xi, facc);
+        }
+      }
+      scr[1] = 0.5 * warp_sum32(facc);
+    }
+
+    // --- J = L^-T in place (upper triangle), thread = column j; a column only depends on L and on
+    //     itself, so no synchronisation is needed between threads while it is built.
+    {
+      const int j = i;
+      const int jmax = min(n - 1, 32 * warp + 31); // last column handled by this warp
+      if(j < n) Jb[j * ldj + j] = rs[j];
+#pragma unroll 1
+      for(int r = jmax - 1; r >= 0; --r)
+      {
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 1
+        for(int k0 = r + 1; k0 <= jmax; k0 += 4)
+        {
+          // accumulator index (k - r - 1) & 3
+          if(k0 <= j) a0 = fma(Jb[k0 * ldj + r], Jb[k0 * ldj + j], a0);
+          if(k0 + 1 <= j) a1 = fma(Jb[(k0 + 1) * ldj + r], Jb[(k0 + 1) * ldj + j], a1);
+          if(k0 + 2 <= j) a2 = fma(Jb[(k0 + 2) * ldj + r], Jb[(k0 + 2) * ldj + j], a2);
+          if(k0 + 3 <= j) a3 = fma(Jb[(k0 + 3) * ldj + r], Jb[(k0 + 3) * ldj + j], a3);
+        }
+        if(r < j && j < n) Jb[r * ldj + j] = (-((a0 + a1) + (a2 + a3))) * rs[r];
+      }
+    }
+    sync();
+    f = scr[1];
+    // clear the strict lower triangle (L is no longer needed), thread = row
+    if(i < n)
+    {
+#pragma unroll 4
+      for(int c = 0; c < i; ++c) Jb[i * ldj + c] = 0.0;
+    }
+    // A_.reset()
+    for(int c = tid; c < m; c += T) stat[c] = ST_INACTIVE;
+    q = 0;
+    sync();
+    return true;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // selectViolatedConstraint_ (src/GoldfarbIdnaniSolver.cpp:84-134), thread = constraint.
+  // Also returns the selected constraint's cx so that computeStepLength_ can reuse it (x is
+  // unchanged between the two when step 1 was executed; same dot4 => same bits).
+  // ------------------------------------------------------------------------------------------
+  __device__ Sel select(double & cx_sel)
+  {
+    double best = 0.0;
+    double bestcx = 0.0;
+    int code = JRLQP_NONE;
+    bool bothneg = false;
+    for(int base = 0; base < mc; base += T)
+    {
+      int c = base + tid;
+      bool act = c < mc && stat[c] == ST_INACTIVE;
+      if(__ballot_sync(JRLQP_FULL, act) == 0u) continue; // warp-uniform
+      const double * ci = Cb + (long long)min(c, mc - 1) * ldC;
+      double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      int k = 0;
+#pragma unroll 2
+      for(; k + 3 < n; k += 4)
+      {
+        c0 = fma(ci[k], xs[k], c0);
+        c1 = fma(ci[k + 1], xs[k + 1], c1);
+        c2 = fma(ci[k + 2], xs[k + 2], c2);
+        c3 = fma(ci[k + 3], xs[k + 3], c3);
+      }
+      if(k < n) c0 = fma(ci[k], xs[k], c0);
+      if(k + 1 < n) c1 = fma(ci[k + 1], xs[k + 1], c1);
+      if(k + 2 < n) c2 = fma(ci[k + 2], xs[k + 2], c2);
+      double cx = (c0 + c1) + (c2 + c3);
+      if(act)
+      {
+        double sl = cx - bl[c];
+        double su = bu[c] - cx;
+        if(sl < 0.0 && su < 0.0) bothneg = true;
+        if(sl < best)
+        {
+          best = sl;
+          bestcx = cx;
+          code = c * 8 + ST_LOWER;
+        }
+        else if(su < best)
+        {
+          best = su;
+          bestcx = cx;
+          code = c * 8 + ST_UPPER;
+        }
+      }
+    }
+    for(int base = 0; base < nb; base += T)
+    {
+      int c = base + tid;
+      if(c < nb && stat[mc + c] == ST_INACTIVE)
+      {
+        double xi = xs[c];
+        double sl = xi - xl[c];
+        double su = xu[c] - xi;
+        if(sl < 0.0 && su < 0.0) bothneg = true;
+        if(sl < best)
+        {
+          best = sl;
+          bestcx = xi;
+          code = (mc + c) * 8 + ST_LOWER_BOUND;
+        }
+        else if(su < best)
+        {
+          best = su;
+          bestcx = xi;
+          code = (mc + c) * 8 + ST_UPPER_BOUND;
+        }
+      }
+    }
+    // first-minimum reduction: smallest value, ties to the smallest constraint index
+#pragma unroll
+    for(int off = 16; off >= 1; off >>= 1)
+    {
+      double ov = __shfl_xor_sync(JRLQP_FULL, best, off);
+      double ocx = __shfl_xor_sync(JRLQP_FULL, bestcx, off);
+      int oc = __shfl_xor_sync(JRLQP_FULL, code, off);
+      if(ov < best || (ov == best && oc < code))
+      {
+        best = ov;
+        bestcx = ocx;
+        code = oc;
+      }
+    }
+    unsigned anyneg = __ballot_sync(JRLQP_FULL, bothneg);
+    if(W > 1)
+    {
+      if(lane == 0)
+      {
+        scr[2 + 2 * warp] = best;
+        scr[3 + 2 * warp] = bestcx;
+        iscr[2 * warp] = code;
+        iscr[2 * warp + 1] = anyneg != 0u;
+      }
+      sync();
+      best = scr[2];
+      bestcx = scr[3];
+      code = iscr[0];
+      int neg = iscr[1];
+#pragma unroll
+      for(int w = 1; w < W; ++w)
+      {
+        double ov = scr[2 + 2 * w];
+        int oc = iscr[2 * w];
+        neg |= iscr[2 * w + 1];
+        if(ov < best || (ov == best && oc < code))
+        {
+          best = ov;
+          bestcx = scr[3 + 2 * w];
+          code = oc;
+        }
+      }
+      anyneg = neg;
+    }
+    else
+    {
+      code = __shfl_sync(JRLQP_FULL, code, 0); // keep control flow uniform even with NaN inputs
+      bestcx = __shfl_sync(JRLQP_FULL, bestcx, 0);
+    }
+    if(anyneg)
+    {
+      Sel s = select_sequential(n, mc, nb, Cb, ldC, xs, bl, bu, xl, xu, stat);
+      cx_sel = s.p < 0 ? 0.0 : (s.p < mc ? dot4_uniform(n, Cb + (long long)s.p * ldC, xs) : xs[s.p - mc]);
+      return s;
+    }
+    cx_sel = bestcx;
+    if(code == JRLQP_NONE) return {-1, ST_INACTIVE};
+    return {code >> 3, code & 7};
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // computeStep_ (src/GoldfarbIdnaniSolver.cpp:136-148): d = J^T n+, z = J2 d2, r = R^-1 d1, and,
+  // speculatively, the Givens recurrence of the addConstraint_ that may follow
+  // (src/GoldfarbIdnaniSolver.cpp:226-232). Leaves d in ds, z in zs, r in rs, the rotation table in
+  // gc/gs and the final rho (the new diagonal entry of R) in scr[10].
+  // ------------------------------------------------------------------------------------------
+  __device__ void compute_step(Sel sc)
+  {
+    const int j = tid;
+    const int jc = min(j, n - 1);
+    const bool general = sc.st < ST_LOWER_BOUND;
+    // stage the selected normal once (coalesced) — it is read by d, c.z and c.x
+    if(general && j < n) cv[j] = Cb[(long long)sc.p * ldC + j];
+    sync();
+
+    // d, thread = column
+    if(general)
+    {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const double * Jc = Jb + jc;
+      int i = 0;
+#pragma unroll 1
+      for(; i + 3 < n; i += 4)
+      {
+        a0 = fma(Jc[i * ldj], cv[i], a0);
+        a1 = fma(Jc[(i + 1) * ldj], cv[i + 1], a1);
+        a2 = fma(Jc[(i + 2) * ldj], cv[i + 2], a2);
+        a3 = fma(Jc[(i + 3) * ldj], cv[i + 3], a3);
+      }
+      if(i < n) a0 = fma(Jc[i * ldj], cv[i], a0);
+      if(i + 1 < n) a1 = fma(Jc[(i + 1) * ldj], cv[i + 1], a1);
+      if(i + 2 < n) a2 = fma(Jc[(i + 2) * ldj], cv[i + 2], a2);
+      double dj = (a0 + a1) + (a2 + a3);
+      if(sc.st == ST_UPPER) dj = -dj;
+      if(j < n) ds[j] = dj;
+    }
+    else
+    {
+      const double * Jrow = Jb + (sc.p - mc) * ldj;
+      if(j < n) ds[j] = sc.st == ST_UPPER_BOUND ? -Jrow[j] : Jrow[j];
+    }
+    sync();
+
+    // z, thread = row: z[i] = dot4_{j=q..n-1}(J(i,j), d[j]), accumulator (j-q)&3
+    {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const double * Jr = Jb + jc * ldj;
+      int c = q;
+#pragma unroll 1
+      for(; c + 3 < n; c += 4)
+      {
+        a0 = fma(Jr[c], ds[c], a0);
+        a1 = fma(Jr[c + 1], ds[c + 1], a1);
+        a2 = fma(Jr[c + 2], ds[c + 2], a2);
+        a3 = fma(Jr[c + 3], ds[c + 3], a3);
+      }
+      if(c < n) a0 = fma(Jr[c], ds[c], a0);
+      if(c + 1 < n) a1 = fma(Jr[c + 1], ds[c + 1], a1);
+      if(c + 2 < n) a2 = fma(Jr[c + 2], ds[c + 2], a2);
+      if(j < n) zs[j] = (a0 + a1) + (a2 + a3);
+    }
+
+    // the two serial recurrences, concurrently on different warps when W > 1
+    if(warp == 0) back_substitution();
+    if(warp == (W > 1 ? 1 : 0)) givens_recurrence();
+    sync();
+  }
+
+  // r = R^-1 d(0:q): column-oriented back substitution with true division, one warp, rows over
+  // the lanes (W slots).
+  __device__ __forceinline__ void back_substitution()
+  {
+    double w[W], rr[W];
+#pragma unroll
+    for(int s = 0; s < W; ++s)
+    {
+      w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
+      rr[s] = 0.0;
+    }
+#pragma unroll 1
+    for(int k = q - 1; k >= 0; --k)
+    {
+      const double * Rk = Rp + colR(k);
+      double rk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31) / Rk[k];
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        if(32 * s >= k + 1) continue; // slot entirely above row k
+        int r = lane + 32 * s;
+        if(r == k)
+          rr[s] = rk;
+        else if(r < k)
+          w[s] = fma(-rk, Rk[r], w[s]);
+      }
+    }
+#pragma unroll
+    for(int s = 0; s < W; ++s)
+      if(lane + 32 * s < q) rs[lane + 32 * s] = rr[s];
+  }
+
+  // Givens recurrence for the sweep i = n-2 .. q (the constraint would become the (q+1)-th).
+  // Serial part: rho_i = r(d[i], rho_{i+1}) — one division and one square root per link, exactly the
+  // operations of Eigen's makeGivens that feed r. The rest of makeGivens (second division, products)
+  // does not feed the recurrence: it is evaluated afterwards, one rotation per lane.
+  __device__ __forceinline__ void givens_recurrence()
+  {
+    double rho = ds[n - 1];
+#pragma unroll 1
+    for(int i = n - 2; i >= q; --i)
+    {
+      const double p = ds[i];
+      double a, u = 1.0, r;
+      int kind;
+      if(rho == 0.0)
+      {
+        kind = 0;
+        a = p;
+        r = fabs(p);
+      }
+      else if(p == 0.0)
+      {
+        kind = 1;
+        a = rho;
+        r = fabs(rho);
+      }
+      else
+      {
+        // |p| > |rho|: t = rho/p, sign and r from p; otherwise t = p/rho, sign and r from rho
+        const bool pg = fabs(p) > fabs(rho);
+        kind = pg ? 2 : 3;
+        const double num = pg ? rho : p;
+        const double den = pg ? p : rho;
+        a = num / den;
+        u = sqrt(fma(a, a, 1.0));
+        if(den < 0.0) u = -u;
+        r = den * u;
+      }
+      if(lane == 0)
+      {
+        // stash (t, u) and what the trivial branches need
+        gc[i] = a;
+        gs[i] = u;
+        gk[i] = kind;
+      }
+      rho = r;
+    }
+    if(lane == 0) scr[10] = rho;
+    __syncwarp();
+#pragma unroll 1
+    for(int i = q + lane; i <= n - 2; i += 32)
+    {
+      const int kind = gk[i];
+      const double a = gc[i];
+      double c, sn;
+      if(kind == 0)
+      {
+        c = a < 0.0 ? -1.0 : 1.0;
+        sn = 0.0;
+      }
+      else if(kind == 1)
+      {
+        c = 0.0;
+        sn = a < 0.0 ? 1.0 : -1.0;
+      }
+      else
+      {
+        // kind 2: c = 1/u, s = -t c ; kind 3: s = -1/u, c = -t s  (-1/u == -(1/u) exactly)
+        const double inv = 1.0 / gs[i];
+        if(kind == 2)
+        {
+          c = inv;
+          sn = -a * c;
+        }
+        else
+        {
+          sn = -inv;
+          c = -a * sn;
+        }
+      }
+      gc[i] = c;
+      gs[i] = sn;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // computeStepLength_ (src/GoldfarbIdnaniSolver.cpp:150-219), incl. the activationStatus(k) quirk.
+  // Evaluated redundantly by every warp (no cross-warp traffic). nz receives
+  // ConstraintNormal::dot(z) (src/GoldfarbIdnaniSolver.cpp:289-293); zpos tells whether ||z|| > 1e-14.
+  // ------------------------------------------------------------------------------------------
+  __device__ void step_length(Sel sc, bool cx_valid, double cx_in, double & t1, double & t2, int & l, double & nz, bool & zpos)
+  {
+    const double big = P.big_bnd;
+    t1 = big;
+    l = 0;
+    {
+      // t1: first minimum of u[k]/r[k] over r[k] > 0 and status_[k] not in {EQUALITY, FIXED}
+      double bt = big;
+      int bl_ = JRLQP_NONE;
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        int k = lane + 32 * s;
+        if(k < q)
+        {
+          int sk = stat[k]; // NOTE: indexed by the position k, as in the reference (quirk)
+          double rk = rs[k];
+          if(sk != ST_EQUALITY && sk != ST_FIXED && rk > 0.0)
+          {
+            double tk = us[k] / rk;
+            if(tk < bt)
+            {
+              bt = tk;
+              bl_ = k;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for(int off = 16; off >= 1; off >>= 1)
+      {
+        double ot = __shfl_xor_sync(JRLQP_FULL, bt, off);
+        int ol = __shfl_xor_sync(JRLQP_FULL, bl_, off);
+        if(ot < bt || (ot == bt && ol < bl_))
+        {
+          bt = ot;
+          bl_ = ol;
+        }
+      }
+      bl_ = __shfl_sync(JRLQP_FULL, bl_, 0);
+      bt = __shfl_sync(JRLQP_FULL, bt, 0);
+      if(bl_ != JRLQP_NONE)
+      {
+        t1 = bt;
+        l = bl_;
+      }
+    }
+
+    // ||z|| with the dot32 order: lane accumulates k = lane, lane+32, ... then the xor butterfly
+    double zz = 0.0;
+    for(int k = lane; k < n; k += 32)
+    {
+      double zk = zs[k];
+      zz = fma(zk, zk, zz);
+    }
+    zpos = sqrt(warp_sum32(zz)) > 1e-14;
+
+    t2 = big;
+    double cz;
+    if(sc.st < ST_LOWER_BOUND)
+    {
+      cz = dot4_uniform(n, cv, zs);
+      nz = sc.st == ST_UPPER ? -cz : cz;
+      if(zpos)
+      {
+        double b = sc.st == ST_UPPER ? bu[sc.p] : bl[sc.p]; // EQUALITY: bl (addInitialConstraint)
+        double cx = cx_valid ? cx_in : dot4_uniform(n, cv, xs);
+        t2 = (b - cx) / cz;
+      }
+    }
+    else
+    {
+      int pb = sc.p - mc;
+      cz = zs[pb];
+      nz = sc.st == ST_UPPER_BOUND ? -cz : cz;
+      if(zpos)
+      {
+        double b = sc.st == ST_UPPER_BOUND ? xu[pb] : xl[pb];
+        t2 = (b - xs[pb]) / cz;
+      }
+    }
+  }
+
+  // x += t z ; f += t (n+.z) (t/2 + u[q]) ; u(0:q) -= t r ; u[q] += t
+  __device__ void take_step(double t, double nz, bool primal)
+  {
+    const double uq = us[q];
+    sync(); // every warp has finished reading x, u, z, r in step_length before they are updated
+    if(primal)
+    {
+      if(tid < n) xs[tid] = fma(t, zs[tid], xs[tid]);
+      f += (t * nz) * (0.5 * t + uq);
+    }
+    if(tid < q) us[tid] = fma(-t, rs[tid], us[tid]);
+    sync(); // everybody has read u[q]
+    if(tid == 0) us[q] = uq + t;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // addConstraint (src/DualSolver.cpp:231-235) + addConstraint_ (src/GoldfarbIdnaniSolver.cpp:221-237):
+  // apply the rotation table built by givens_recurrence(), thread = row of J, the rotated value
+  // of column i+1 is carried in a register from one rotation to the next.
+  // ------------------------------------------------------------------------------------------
+  __device__ void add_constraint(Sel sc)
+  {
+    if(tid == 0)
+    {
+      alist[q] = sc.p;
+      stat[sc.p] = (signed char)sc.st;
+    }
+    q += 1;
+    if(tid < n)
+    {
+      double * Jr = Jb + tid * ldj;
+      if(q - 1 <= n - 2)
+      {
+        double y = Jr[n - 1];
+#pragma unroll 2
+        for(int i = n - 2; i >= q - 1; --i)
+        {
+          const double c = gc[i], sn = gs[i];
+          const double xi = Jr[i];
+          Jr[i + 1] = fma(c, y, sn * xi);
+          y = fma(c, xi, -(sn * y));
+        }
+        Jr[q - 1] = y;
+      }
+      // R(0:q, q-1) = d(0:q), with d[q-1] = rho
+      if(tid < q) Rp[colR(q - 1) + tid] = tid == q - 1 ? scr[10] : ds[tid];
+    }
+    sync();
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // removeConstraint (src/DualSolver.cpp:237-244) + removeConstraint_ (src/GoldfarbIdnaniSolver.cpp:239-256).
+  // Rare (about one per solve): done by warp 0 alone, rows / columns over its lanes (W slots).
+  // ------------------------------------------------------------------------------------------
+  __device__ void remove_constraint(int l)
+  {
+    sync();
+    if(warp == 0)
+    {
+      // u.segment(l, q-l) = u.tail(q-l) (u has q+1 entries) ; A_.deactivate(l)
+      double ut[W];
+      int at[W];
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        int k = lane + 32 * s;
+        ut[s] = (k >= l && k < q) ? us[k + 1] : 0.0;
+        at[s] = (k >= l && k + 1 < q) ? alist[k + 1] : -1;
+      }
+      int removed = alist[l];
+      __syncwarp();
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        int k = lane + 32 * s;
+        if(k >= l && k < q) us[k] = ut[s];
+        if(k >= l && k + 1 < q) alist[k] = at[s];
+      }
+      if(lane == 0) stat[removed] = ST_INACTIVE;
+      const int qn = q - 1;
+      __syncwarp();
+#pragma unroll 1
+      for(int i = l; i < qn; ++i)
+      {
+        double * Ri = Rp + colR(i);
+        double * Ri1 = Rp + colR(i + 1);
+        // R.col(i).head(i) = R.col(i+1).head(i)
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          int k = lane + 32 * s;
+          if(k < i) Ri[k] = Ri1[k];
+        }
+        double c, sn, r;
+        make_givens(Ri1[i], Ri1[i + 1], c, sn, r);
+        __syncwarp();
+        if(lane == 0) Ri[i] = r;
+        // rows i, i+1 of columns i+2 .. q (lane = column)
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          int j = i + 2 + lane + 32 * s;
+          if(j <= qn)
+          {
+            double * Rj = Rp + colR(j);
+            double xi = Rj[i], yi = Rj[i + 1];
+            Rj[i] = fma(c, xi, -(sn * yi));
+            Rj[i + 1] = fma(c, yi, sn * xi);
+          }
+        }
+        // columns i, i+1 of J (lane = row)
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          int rrow = lane + 32 * s;
+          if(rrow < n)
+          {
+            double * Jr = Jb + rrow * ldj;
+            double xi = Jr[i], yi = Jr[i + 1];
+            Jr[i] = fma(c, xi, -(sn * yi));
+            Jr[i + 1] = fma(c, yi, sn * xi);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    q -= 1;
+    sync();
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // DualSolver::solve (src/DualSolver.cpp:91-168) for problem b, with initActiveSet /
+  // addInitialConstraint (src/GoldfarbIdnaniSolver.cpp:268-338) folded into the same loop: the
+  // pre-activation of an equality (or fixed variable) is a step whose constraint is given instead
+  // of selected, whose length is the exact step onto the constraint, and which always ends with an
+  // add. One loop body => one copy of every phase in the instruction stream (the kernel is
+  // instruction-cache sensitive, see profiles/r01b_*).
+  // ------------------------------------------------------------------------------------------
+  __device__ void solve(long long b)
+  {
+    bl = P.bl + b * P.sbl;
+    bu = P.bu + b * P.sbu;
+    xl = nb ? P.xl + b * P.sxl : nullptr;
+    xu = nb ? P.xu + b * P.sxu : nullptr;
+    if(STAGE_C)
+    {
+      Cb = Cs;
+      ldC = P.ldcs;
+    }
+    else
+    {
+      Cb = P.C + b * P.sC;
+      ldC = P.ldc;
+    }
+
+    if(!init(b))
+    {
+      write_failure(b, TS_NON_POS_HESSIAN);
+      return;
+    }
+
+    int status = TS_MAX_ITER_REACHED;
+    int it = 0;
+    int cursor = 0; // next constraint / bound to test for pre-activation; m when that phase is over
+    bool skip = false;
+    Sel sc{-1, ST_INACTIVE};
+    double cx_sel = 0.0;
+    const double big = P.big_bnd;
+#pragma unroll 1
+    for(;;)
+    {
+      bool pre = false;
+      // initActiveSet: equalities (bl == bu) in order, then fixed variables (xl == xu) in order
+      while(cursor < m)
+      {
+        const int c = cursor++;
+        if(c < mc ? (bl[c] == bu[c]) : (xl[c - mc] == xu[c - mc]))
+        {
+          sc = {c, c < mc ? ST_EQUALITY : ST_FIXED};
+          pre = true;
+          break;
+        }
+      }
+      if(!pre)
+      {
+        if(it >= P.max_iter) break; // MAX_ITER_REACHED
+        if(!skip)
+        {
+          sc = select(cx_sel);
+          if(sc.st == ST_INACTIVE)
+          {
+            status = TS_SUCCESS;
+            break;
+          }
+        }
+      }
+      if(pre || !skip)
+      {
+        if(tid == 0) us[q] = 0.0; // published by the barriers of compute_step
+      }
+      compute_step(sc);
+      double t1, t2, nz;
+      int l;
+      bool zpos;
+      step_length(sc, !pre && !skip, cx_sel, t1, t2, l, nz, zpos);
+      double t;
+      bool primal = true, add = true;
+      if(pre)
+        t = zpos ? t2 : 0.0; // exact step onto the constraint (src/GoldfarbIdnaniSolver.cpp:307-322)
+      else
+      {
+        t = t2 < t1 ? t2 : t1; // std::min(t1, t2)
+        if(t >= big)
+        {
+          status = TS_INFEASIBLE;
+          break;
+        }
+        if(t2 >= big)
+          primal = add = false; // dual-only step, then drop
+        else
+          add = t == t2; // full step -> add ; partial step -> drop
+      }
+      take_step(t, nz, primal);
+      if(add)
+        add_constraint(sc);
+      else
+        remove_constraint(l);
+      if(!pre)
+      {
+        skip = !add;
+        ++it;
+      }
+    }
+    sync();
+    write_result(b, status, it);
+  }
+
+  __device__ void write_result(long long b, int status, int it)
+  {
+    double * xo = P.x + b * n;
+    for(int i = tid; i < n; i += T) xo[i] = xs[i];
+    if(P.u)
+    {
+      // DualSolver::multipliers (src/DualSolver.cpp:38-69): thread i looks for itself in the active list
+      double * uo = P.u + b * m;
+      for(int i = tid; i < m; i += T)
+      {
+        int s = stat[i];
+        double v = 0.0;
+        if(s != ST_INACTIVE)
+        {
+          for(int k = 0; k < q; ++k)
+            if(alist[k] == i) v = (s == ST_UPPER || s == ST_UPPER_BOUND) ? us[k] : -us[k];
+        }
+        uo[i] = v;
+      }
+    }
+    if(P.active_set)
+    {
+      signed char * ao = P.active_set + b * m;
+      for(int i = tid; i < m; i += T) ao[i] = stat[i];
+    }
+    if(P.active_list)
+    {
+      int * lo = P.active_list + b * n;
+      for(int k = tid; k < n; k += T) lo[k] = k < q ? alist[k] : -1;
+    }
+    if(tid == 0)
+    {
+      if(P.f) P.f[b] = f;
+      if(P.iterations) P.iterations[b] = it;
+      if(P.status) P.status[b] = status;
+      if(P.n_active) P.n_active[b] = q;
+    }
+  }
+
+  __device__ void write_failure(long long b, int status)
+  {
+    double * xo = P.x + b * n;
+    for(int i = tid; i < n; i += T) xo[i] = 0.0;
+    if(P.u)
+      for(int i = tid; i < m; i += T) P.u[b * m + i] = 0.0;
+    if(P.active_set)
+      for(int i = tid; i < m; i += T) P.active_set[b * m + i] = ST_INACTIVE;
+    if(P.active_list)
+      for(int k = tid; k < n; k += T) P.active_list[b * n + k] = -1;
+    if(tid == 0)
+    {
+      if(P.f) P.f[b] = 0.0;
+      if(P.iterations) P.iterations[b] = 0;
+      if(P.status) P.status[b] = status;
+      if(P.n_active) P.n_active[b] = 0;
+    }
+  }
+};
+
+// Persistent kernel: grid = resident CTAs of the whole GPU; every CTA pulls the next problem index
+// from an atomic ticket counter, which absorbs the divergent iteration counts across QPs.
+template<int W, bool STAGE_C>
+__global__ void __launch_bounds__(32 * W) gi_dense_cta_kernel(const GiParams p)
+{
+  extern __shared__ __align__(16) double smem[];
+  GiCta<W, STAGE_C> cta(p, smem);
+  unsigned long long * ticket = reinterpret_cast<unsigned long long *>(smem + p.off_scr + 12);
+  for(;;)
+  {
+    if(threadIdx.x == 0) *ticket = atomicAdd(p.counter, 1ull);
+    cta.sync();
+    const unsigned long long b = *ticket;
+    if(b >= (unsigned long long)p.batch) break;
+    cta.solve((long long)b);
+    cta.sync();
+  }
+}
+
+} // namespace jrlqp

@@ -67,8 +67,9 @@ struct GiParams
   // shared-memory layout (computed on the host, in doubles unless noted)
   int ldj; // leading dimension of the row-major J/L buffer (odd => conflict-free row-strided access)
   int ldcs; // leading dimension of the staged C (odd), if staged
-  int npad; // 32 * rows_per_thread
-  int off_R, off_x, off_z, off_d, off_r, off_u, off_C, off_alist, off_stat; // offsets in doubles
+  int npad; // threads per CTA (>= n)
+  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_ldiag, off_scr, off_C; // offsets in doubles
+  int off_alist, off_gk, off_iscr, off_stat; // offsets in doubles of the int / int8 arrays
 };
 
 } // namespace jrlqp
