@@ -43,7 +43,7 @@ KernelFn pick_kernel(int warps, bool stage)
 struct Layout
 {
   int ldj, ldcs, npad;
-  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_ldiag, off_scr, off_C;
+  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_scr, off_C;
   int off_alist, off_gk, off_iscr, off_stat;
   int total_doubles;
 };
@@ -74,6 +74,9 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage)
   o += np;
   L.off_gs = o;
   o += np;
+  o += o & 1; // 16-byte alignment of the (c, s) pairs
+  L.off_gcs = o;
+  o += 2 * np;
   L.off_ldiag = o;
   o += np;
   L.off_scr = o;
@@ -371,6 +374,7 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.off_cv = s->lay.off_cv;
   p.off_gc = s->lay.off_gc;
   p.off_gs = s->lay.off_gs;
+  p.off_gcs = s->lay.off_gcs;
   p.off_ldiag = s->lay.off_ldiag;
   p.off_scr = s->lay.off_scr;
   p.off_C = s->lay.off_C;

@@ -190,6 +190,7 @@ struct GiCta
   const int tid, lane, warp;
   const int n, mc, nb, m, ldj;
   double *Jb, *Rp, *xs, *zs, *ds, *rs, *us, *cv, *gc, *gs, *ldiag, *Cs, *scr;
+  double2 * gcs; // (c, s) rotation table of the Givens sweep
   int * alist;
   int * gk;
   int * iscr;
@@ -214,6 +215,7 @@ struct GiCta
     cv = smem + p.off_cv;
     gc = smem + p.off_gc;
     gs = smem + p.off_gs;
+    gcs = reinterpret_cast<double2 *>(smem + p.off_gcs);
     ldiag = smem + p.off_ldiag;
     scr = smem + p.off_scr;
     Cs = smem + p.off_C;
@@ -714,8 +716,7 @@ struct GiCta
           c = -a * sn;
         }
       }
-      gc[i] = c;
-      gs[i] = sn;
+      gcs[i] = make_double2(c, sn);
     }
   }
 
@@ -785,12 +786,27 @@ struct GiCta
     double cz;
     if(sc.st < ST_LOWER_BOUND)
     {
-      cz = dot4_uniform(n, cv, zs);
+      // dot4(c, z) and dot4(c, x): accumulator t = sum over k = t, t+4, ... (ascending) is an
+      // independent chain, so lane t runs chain t of c.z and lane 4+t chain t of c.x; the result is
+      // (a0 + a1) + (a2 + a3), exactly the canonical dot4.
+      const double * v = (lane & 4) ? xs : zs;
+      double acc = 0.0;
+      if(lane < 8)
+      {
+#pragma unroll 2
+        for(int k = lane & 3; k < n; k += 4) acc = fma(cv[k], v[k], acc);
+      }
+      const double a1 = __shfl_down_sync(JRLQP_FULL, acc, 1);
+      const double s01 = acc + a1; // valid on lanes 0, 2, 4, 6
+      const double s23 = __shfl_down_sync(JRLQP_FULL, s01, 2);
+      const double dot = s01 + s23; // valid on lanes 0 (c.z) and 4 (c.x)
+      cz = __shfl_sync(JRLQP_FULL, dot, 0);
+      const double cxn = __shfl_sync(JRLQP_FULL, dot, 4);
       nz = sc.st == ST_UPPER ? -cz : cz;
       if(zpos)
       {
         double b = sc.st == ST_UPPER ? bu[sc.p] : bl[sc.p]; // EQUALITY: bl (addInitialConstraint)
-        double cx = cx_valid ? cx_in : dot4_uniform(n, cv, xs);
+        double cx = cx_valid ? cx_in : cxn;
         t2 = (b - cx) / cz;
       }
     }
@@ -844,7 +860,8 @@ struct GiCta
 #pragma unroll 2
         for(int i = n - 2; i >= q - 1; --i)
         {
-          const double c = gc[i], sn = gs[i];
+          const double2 cs2 = gcs[i];
+          const double c = cs2.x, sn = cs2.y;
           const double xi = Jr[i];
           Jr[i + 1] = fma(c, y, sn * xi);
           y = fma(c, xi, -(sn * y));
@@ -1106,7 +1123,7 @@ struct GiCta
 // Persistent kernel: grid = resident CTAs of the whole GPU; every CTA pulls the next problem index
 // from an atomic ticket counter, which absorbs the divergent iteration counts across QPs.
 template<int W, bool STAGE_C>
-__global__ void __launch_bounds__(32 * W) gi_dense_cta_kernel(const GiParams p)
+__global__ void __launch_bounds__(32 * W, (W == 1 ? 24 : (W == 2 ? 6 : 1))) gi_dense_cta_kernel(const GiParams p)
 {
   extern __shared__ __align__(16) double smem[];
   GiCta<W, STAGE_C> cta(p, smem);
