@@ -182,6 +182,104 @@ int jrlqp_version(void);
  * TFLOP/s (2 flops per FMA), or a negative error. Used by bench.py for the roofline denominator. */
 double jrlqp_measure_fp64_tflops(int32_t device, int32_t repeats);
 
+/* ------------------------------------------------------------------------------------------------
+ * Structured Cholesky decompositions (north-star item 4), batched: `batch` matrices that share ONE
+ * block structure are factorised / solved by one call, one instance per CTA.
+ *
+ * Replaces structured::StructuredG (include/jrl-qp/structured/StructuredG.h:14-76,
+ * src/structured/StructuredG.cpp:6-113) and the functions it dispatches to:
+ *   decomposition::triBlockDiagLLT / triBlockDiagLSolve / triBlockDiagLTransposeSolve
+ *       (include/jrl-qp/decomposition/triBlockDiagLLT.h:41-72, src/decomposition/triBlockDiagLLT.cpp)
+ *   decomposition::blockArrowLLT / blockArrowLSolve / blockArrowLTransposeSolve
+ *       (include/jrl-qp/decomposition/blockArrowLLT.h:72-110, src/decomposition/blockArrowLLT.cpp)
+ * The reference passes std::vector<MatrixRef> views; the descriptor below carries the same views
+ * as (element offset from the instance base, leading dimension) per block, so blocks may be views
+ * into a dense matrix (tests/triBlockDiagLLTTest.cpp:41-43) or packed tiles.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* structured::StructuredG::Type (include/jrl-qp/structured/StructuredG.h:17-22), same order */
+enum jrlqp_structure_type
+{
+  JRLQP_TRI_BLOCK_DIAGONAL = 0,
+  JRLQP_BLOCK_ARROW_UP = 1,
+  JRLQP_BLOCK_ARROW_DOWN = 2
+};
+
+/* HOST arrays (copied at create). Diagonal block i is block_size[i] x block_size[i] (lower triangle
+ * read and written; the upper part "remains whatever was there", triBlockDiagLLT.h:37-39).
+ * Off-diagonal block i (i < nblocks-1), column-major with leading dimension off_ld[i]:
+ *   TRI_BLOCK_DIAGONAL  S_i  n_{i+1} x n_i   sub-diagonal block (i+1, i)
+ *   BLOCK_ARROW_DOWN    S_i  n_{b-1} x n_i   block of the last block row
+ *   BLOCK_ARROW_UP      S_i  n_{i+1} x n_0   block of the first block column (holds B_i^T afterwards)
+ */
+typedef struct jrlqp_structure
+{
+  int32_t type; /* jrlqp_structure_type */
+  int32_t nblocks;
+  const int32_t * block_size; /* [nblocks]   */
+  const int64_t * diag_offset; /* [nblocks]   elements from the instance base */
+  const int32_t * diag_ld; /* [nblocks]   */
+  const int64_t * off_offset; /* [nblocks-1] */
+  const int32_t * off_ld; /* [nblocks-1] */
+} jrlqp_structure;
+
+typedef struct jrlqp_structured jrlqp_structured;
+
+/* StructuredG(Type, diag, offDiag) (src/structured/StructuredG.cpp:6-20). batch_capacity bounds
+ * the *_host entry points (device staging is allocated on first use). Blocks up to 96 rows
+ * (three tiles of the largest block must fit in the 227 KB of shared memory of one SM). */
+int jrlqp_structured_create(jrlqp_structured ** out, const jrlqp_structure * st, int64_t batch_capacity, int32_t device);
+int jrlqp_structured_destroy(jrlqp_structured * s);
+const char * jrlqp_structured_last_error(const jrlqp_structured * s);
+
+/* StructuredG::lltInPlace (src/structured/StructuredG.cpp:22-43), in place on `data`
+ * (instance k at data + k * stride). ok[k] (nullable) = 1 if decomposed, 0 if a diagonal block was
+ * not positive definite (the reference returns false; the failing block and the ones after it are
+ * then unspecified). DEVICE pointers, asynchronous on `stream`. */
+int jrlqp_structured_llt_device(jrlqp_structured * s, double * data, int64_t stride, int64_t batch, int32_t * ok, void * stream);
+/* Same with HOST pointers (H2D, kernel, D2H, synchronise). Returns the number of instances that
+ * failed (>= 0) or a negative JRLQP_ERR_*. */
+int jrlqp_structured_llt_host(jrlqp_structured * s, double * data, int64_t stride, int64_t batch, int32_t * ok);
+
+/* StructuredG::solveL (transpose = 0: X = (P L)^-1 M, src/structured/StructuredG.cpp:66-113) and
+ * StructuredG::solveInPlaceLTranspose (transpose = 1: X = P L^-T M, :45-64), in place on M
+ * (n x ncols column-major, leading dimension ldm, instance k at M + k * m_stride). start / end are
+ * the reference's hints: rows [start, end) of M are the only non-zero ones (end < 0: none given);
+ * they only skip work, results are those of the plain call. `data` holds the factor. */
+int jrlqp_structured_solve_device(jrlqp_structured * s,
+                                  const double * data,
+                                  int64_t stride,
+                                  double * M,
+                                  int32_t ldm,
+                                  int32_t ncols,
+                                  int64_t m_stride,
+                                  int64_t batch,
+                                  int32_t transpose,
+                                  int32_t start,
+                                  int32_t end,
+                                  void * stream);
+int jrlqp_structured_solve_host(jrlqp_structured * s,
+                                const double * data,
+                                int64_t stride,
+                                double * M,
+                                int32_t ldm,
+                                int32_t ncols,
+                                int64_t m_stride,
+                                int64_t batch,
+                                int32_t transpose,
+                                int32_t start,
+                                int32_t end);
+/* threads per instance, resident instances per SM and shared memory per instance of the two kernels */
+typedef struct jrlqp_structured_info
+{
+  int32_t threads;
+  int32_t llt_smem_bytes, llt_ctas_per_sm;
+  int32_t solve_smem_bytes, solve_ctas_per_sm;
+  int32_t num_sms;
+  int64_t elements_per_instance; /* doubles of the factor actually touched (algorithmic bytes / 8) */
+} jrlqp_structured_info;
+int jrlqp_structured_get_info(const jrlqp_structured * s, jrlqp_structured_info * info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,14 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage)
 
 } // namespace
 
+namespace jrlqp
+{
+void count_launch()
+{
+  g_launches.fetch_add(1);
+}
+} // namespace jrlqp
+
 struct jrlqp_solver
 {
   int n = 0, mc = 0, nb = 0, m = 0;

@@ -1,0 +1,359 @@
+// Host side of the structured-decomposition C-ABI (include/jrlqp_b200.h, jrlqp_structured_*):
+// descriptor upload, launch configuration, and the host-pointer entry points. Pure CUDA runtime.
+#include "structured.cuh"
+
+#include "jrlqp_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+using namespace jrlqp;
+
+namespace jrlqp
+{
+void count_launch(); // capi.cu: feeds jrlqp_launch_count()
+}
+
+struct jrlqp_structured
+{
+  int type = 0, b = 0, n = 0, nmax = 0;
+  long long capacity = 0;
+  int device = 0;
+  int threads = 32;
+  int num_sms = 0;
+  int llt_smem = 0, solve_smem = 0, llt_occ = 0, solve_occ = 0;
+  long long touched = 0;
+  std::vector<int> size, dld, old, start;
+  std::vector<long long> doff, ooff;
+  long long min_stride = 0; // one past the last element any block touches
+  // device copies of the descriptor
+  int *d_size = nullptr, *d_dld = nullptr, *d_old = nullptr, *d_start = nullptr;
+  long long *d_doff = nullptr, *d_ooff = nullptr;
+  // staging for the host entry points
+  double * d_data = nullptr;
+  long long d_data_elems = 0;
+  double * d_M = nullptr;
+  long long d_M_elems = 0;
+  int * d_ok = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  bool check(cudaError_t e, const char * what)
+  {
+    if(e == cudaSuccess) return true;
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+  }
+};
+
+#define SCK(call)                                       \
+  do                                                    \
+  {                                                     \
+    if(!s->check((call), #call)) return JRLQP_ERR_CUDA; \
+  } while(0)
+
+namespace
+{
+
+void off_shape(const jrlqp_structured * s, int i, int & rows, int & cols)
+{
+  if(s->type == SG_TRI)
+  {
+    rows = s->size[i + 1];
+    cols = s->size[i];
+  }
+  else if(s->type == SG_ARROW_DOWN)
+  {
+    rows = s->size[s->b - 1];
+    cols = s->size[i];
+  }
+  else
+  {
+    rows = s->size[i + 1];
+    cols = s->size[0];
+  }
+}
+
+StructParams base_params(const jrlqp_structured * s)
+{
+  StructParams p{};
+  p.type = s->type;
+  p.b = s->b;
+  p.n = s->n;
+  p.nmax = s->nmax;
+  p.size = s->d_size;
+  p.doff = s->d_doff;
+  p.dld = s->d_dld;
+  p.ooff = s->d_ooff;
+  p.old = s->d_old;
+  p.start = s->d_start;
+  return p;
+}
+
+template<class T>
+cudaError_t upload(T *& d, const std::vector<T> & h)
+{
+  cudaError_t e = cudaMalloc(&d, sizeof(T) * std::max<size_t>(h.size(), 1));
+  if(e != cudaSuccess) return e;
+  if(h.empty()) return cudaSuccess;
+  return cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
+}
+
+} // namespace
+
+extern "C"
+{
+
+int jrlqp_structured_create(jrlqp_structured ** out, const jrlqp_structure * st, int64_t batch_capacity, int32_t device)
+{
+  if(!out) return JRLQP_ERR_ARG;
+  *out = nullptr;
+  if(!st || st->nblocks < 1 || st->type < 0 || st->type > 2 || batch_capacity < 0) return JRLQP_ERR_ARG;
+  if(!st->block_size || !st->diag_offset || !st->diag_ld) return JRLQP_ERR_ARG;
+  if(st->nblocks > 1 && (!st->off_offset || !st->off_ld)) return JRLQP_ERR_ARG;
+  jrlqp_structured * s = new jrlqp_structured();
+  *out = s;
+  s->type = st->type;
+  s->b = st->nblocks;
+  s->capacity = batch_capacity;
+  s->device = device;
+  s->start.push_back(0);
+  for(int i = 0; i < s->b; ++i)
+  {
+    const int ni = st->block_size[i];
+    if(ni < 1 || ni > 96 || st->diag_ld[i] < ni || st->diag_offset[i] < 0)
+    {
+      s->err = "invalid diagonal block (size must be in [1, 96], ld >= size)";
+      return JRLQP_ERR_ARG;
+    }
+    s->size.push_back(ni);
+    s->doff.push_back(st->diag_offset[i]);
+    s->dld.push_back(st->diag_ld[i]);
+    s->n += ni;
+    s->start.push_back(s->n);
+    s->nmax = std::max(s->nmax, ni);
+    s->min_stride = std::max<long long>(s->min_stride, st->diag_offset[i] + (long long)(ni - 1) * st->diag_ld[i] + ni);
+    s->touched += (long long)ni * (ni + 1) / 2;
+  }
+  for(int i = 0; i + 1 < s->b; ++i)
+  {
+    int rows, cols;
+    off_shape(s, i, rows, cols);
+    if(st->off_ld[i] < rows || st->off_offset[i] < 0)
+    {
+      s->err = "invalid off-diagonal block (ld < rows)";
+      return JRLQP_ERR_ARG;
+    }
+    s->ooff.push_back(st->off_offset[i]);
+    s->old.push_back(st->off_ld[i]);
+    s->min_stride = std::max<long long>(s->min_stride, st->off_offset[i] + (long long)(cols - 1) * st->off_ld[i] + rows);
+    s->touched += (long long)rows * cols;
+  }
+  int ndev = 0;
+  SCK(cudaGetDeviceCount(&ndev));
+  if(device < 0 || device >= ndev)
+  {
+    s->err = "no such CUDA device";
+    return JRLQP_ERR_CUDA;
+  }
+  SCK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SCK(cudaGetDeviceProperties(&prop, device));
+  if(prop.major != 10)
+  {
+    s->err = "this library contains sm_100a code only (Blackwell B200 required)";
+    return JRLQP_ERR_CUDA;
+  }
+  s->num_sms = prop.multiProcessorCount;
+  s->threads = s->nmax <= 32 ? 32 : (s->nmax <= 64 ? 64 : 128);
+  const int tile = s->nmax * s->nmax;
+  s->llt_smem = (3 * tile + s->nmax + 2) * 8;
+  s->solve_smem = (((s->n + 1) & ~1) + 2 * tile) * 8;
+  if(std::max(s->llt_smem, s->solve_smem) > (int)prop.sharedMemPerBlockOptin)
+  {
+    s->err = "structure does not fit in shared memory";
+    return JRLQP_ERR_ARG;
+  }
+  SCK(cudaFuncSetAttribute(structured_llt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->llt_smem));
+  SCK(cudaFuncSetAttribute(structured_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->solve_smem));
+  SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->llt_occ, structured_llt_kernel, s->threads, s->llt_smem));
+  SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->solve_occ, structured_solve_kernel, s->threads, s->solve_smem));
+  if(s->llt_occ < 1 || s->solve_occ < 1)
+  {
+    s->err = "kernel cannot be made resident";
+    return JRLQP_ERR_ARG;
+  }
+  SCK(upload(s->d_size, s->size));
+  SCK(upload(s->d_dld, s->dld));
+  SCK(upload(s->d_old, s->old));
+  SCK(upload(s->d_start, s->start));
+  SCK(upload(s->d_doff, s->doff));
+  SCK(upload(s->d_ooff, s->ooff));
+  SCK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  return JRLQP_OK;
+}
+
+int jrlqp_structured_destroy(jrlqp_structured * s)
+{
+  if(!s) return JRLQP_OK;
+  cudaSetDevice(s->device);
+  void * ptrs[] = {s->d_size, s->d_dld, s->d_old, s->d_start, s->d_doff, s->d_ooff, s->d_data, s->d_M, s->d_ok};
+  for(void * p : ptrs)
+    if(p) cudaFree(p);
+  if(s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return JRLQP_OK;
+}
+
+const char * jrlqp_structured_last_error(const jrlqp_structured * s)
+{
+  return s ? s->err.c_str() : "null handle";
+}
+
+int jrlqp_structured_get_info(const jrlqp_structured * s, jrlqp_structured_info * info)
+{
+  if(!s || !info) return JRLQP_ERR_ARG;
+  info->threads = s->threads;
+  info->llt_smem_bytes = s->llt_smem;
+  info->llt_ctas_per_sm = s->llt_occ;
+  info->solve_smem_bytes = s->solve_smem;
+  info->solve_ctas_per_sm = s->solve_occ;
+  info->num_sms = s->num_sms;
+  info->elements_per_instance = s->touched;
+  return JRLQP_OK;
+}
+
+int jrlqp_structured_llt_device(jrlqp_structured * s, double * data, int64_t stride, int64_t batch, int32_t * ok, void * stream)
+{
+  if(!s || !data || batch < 0) return JRLQP_ERR_ARG;
+  if(batch > 1 && stride < s->min_stride) return JRLQP_ERR_ARG; // instances would overlap
+  if(batch == 0) return JRLQP_OK;
+  SCK(cudaSetDevice(s->device));
+  StructParams p = base_params(s);
+  p.data = data;
+  p.stride = stride;
+  p.batch = batch;
+  p.ok = ok;
+  const long long grid = std::min<long long>(batch, (long long)s->llt_occ * s->num_sms);
+  structured_llt_kernel<<<(unsigned)grid, s->threads, s->llt_smem, (cudaStream_t)stream>>>(p);
+  count_launch();
+  SCK(cudaGetLastError());
+  return JRLQP_OK;
+}
+
+int jrlqp_structured_solve_device(jrlqp_structured * s,
+                                  const double * data,
+                                  int64_t stride,
+                                  double * M,
+                                  int32_t ldm,
+                                  int32_t ncols,
+                                  int64_t m_stride,
+                                  int64_t batch,
+                                  int32_t transpose,
+                                  int32_t start,
+                                  int32_t end,
+                                  void * stream)
+{
+  if(!s || !data || !M || batch < 0 || ncols < 0 || ldm < s->n) return JRLQP_ERR_ARG;
+  if(start < 0 || start > s->n || end > s->n) return JRLQP_ERR_ARG;
+  if(batch == 0 || ncols == 0) return JRLQP_OK;
+  SCK(cudaSetDevice(s->device));
+  StructParams p = base_params(s);
+  p.data = const_cast<double *>(data);
+  p.stride = stride;
+  p.batch = batch;
+  p.M = M;
+  p.ldm = ldm;
+  p.ncols = ncols;
+  p.mstride = m_stride;
+  p.transpose = transpose ? 1 : 0;
+  p.hint_start = start;
+  p.hint_end = end;
+  const long long grid = std::min<long long>(batch * ncols, (long long)s->solve_occ * s->num_sms);
+  structured_solve_kernel<<<(unsigned)grid, s->threads, s->solve_smem, (cudaStream_t)stream>>>(p);
+  count_launch();
+  SCK(cudaGetLastError());
+  return JRLQP_OK;
+}
+
+static int ensure_data(jrlqp_structured * s, long long elems)
+{
+  if(elems > s->d_data_elems)
+  {
+    if(s->d_data) cudaFree(s->d_data);
+    s->d_data = nullptr;
+    s->d_data_elems = 0;
+    SCK(cudaMalloc(&s->d_data, sizeof(double) * elems));
+    s->d_data_elems = elems;
+  }
+  if(!s->d_ok) SCK(cudaMalloc(&s->d_ok, sizeof(int) * std::max<long long>(s->capacity, 1)));
+  return JRLQP_OK;
+}
+
+int jrlqp_structured_llt_host(jrlqp_structured * s, double * data, int64_t stride, int64_t batch, int32_t * ok)
+{
+  if(!s || !data || batch < 0) return JRLQP_ERR_ARG;
+  if(batch > s->capacity) return JRLQP_ERR_CAPACITY;
+  if(batch == 0) return 0;
+  if(stride < s->min_stride) return JRLQP_ERR_ARG;
+  SCK(cudaSetDevice(s->device));
+  const long long elems = (long long)batch * stride;
+  int rc = ensure_data(s, elems);
+  if(rc != JRLQP_OK) return rc;
+  SCK(cudaMemcpyAsync(s->d_data, data, sizeof(double) * elems, cudaMemcpyHostToDevice, s->stream));
+  rc = jrlqp_structured_llt_device(s, s->d_data, stride, batch, s->d_ok, s->stream);
+  if(rc != JRLQP_OK) return rc;
+  SCK(cudaMemcpyAsync(data, s->d_data, sizeof(double) * elems, cudaMemcpyDeviceToHost, s->stream));
+  std::vector<int> hok((size_t)batch);
+  SCK(cudaMemcpyAsync(hok.data(), s->d_ok, sizeof(int) * batch, cudaMemcpyDeviceToHost, s->stream));
+  SCK(cudaStreamSynchronize(s->stream));
+  int failed = 0;
+  for(long long k = 0; k < batch; ++k)
+  {
+    if(ok) ok[k] = hok[(size_t)k];
+    failed += hok[(size_t)k] ? 0 : 1;
+  }
+  return failed;
+}
+
+int jrlqp_structured_solve_host(jrlqp_structured * s,
+                                const double * data,
+                                int64_t stride,
+                                double * M,
+                                int32_t ldm,
+                                int32_t ncols,
+                                int64_t m_stride,
+                                int64_t batch,
+                                int32_t transpose,
+                                int32_t start,
+                                int32_t end)
+{
+  if(!s || !data || !M || batch < 0 || ncols < 0 || ldm < s->n) return JRLQP_ERR_ARG;
+  if(batch > s->capacity) return JRLQP_ERR_CAPACITY;
+  if(batch == 0 || ncols == 0) return JRLQP_OK;
+  if(stride < s->min_stride || m_stride < (long long)(ncols - 1) * ldm + s->n) return JRLQP_ERR_ARG;
+  SCK(cudaSetDevice(s->device));
+  const long long elems = (long long)batch * stride;
+  int rc = ensure_data(s, elems);
+  if(rc != JRLQP_OK) return rc;
+  const long long melems = (long long)batch * m_stride;
+  if(melems > s->d_M_elems)
+  {
+    if(s->d_M) cudaFree(s->d_M);
+    s->d_M = nullptr;
+    s->d_M_elems = 0;
+    SCK(cudaMalloc(&s->d_M, sizeof(double) * melems));
+    s->d_M_elems = melems;
+  }
+  SCK(cudaMemcpyAsync(s->d_data, data, sizeof(double) * elems, cudaMemcpyHostToDevice, s->stream));
+  SCK(cudaMemcpyAsync(s->d_M, M, sizeof(double) * melems, cudaMemcpyHostToDevice, s->stream));
+  rc = jrlqp_structured_solve_device(s, s->d_data, stride, s->d_M, ldm, ncols, m_stride, batch, transpose, start, end, s->stream);
+  if(rc != JRLQP_OK) return rc;
+  SCK(cudaMemcpyAsync(M, s->d_M, sizeof(double) * melems, cudaMemcpyDeviceToHost, s->stream));
+  SCK(cudaStreamSynchronize(s->stream));
+  return JRLQP_OK;
+}
+
+} // extern "C"

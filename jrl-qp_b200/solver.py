@@ -106,6 +106,9 @@ EXPORTED_SYMBOLS = [
     "jrlqp_version", "jrlqp_default_options", "jrlqp_create", "jrlqp_destroy", "jrlqp_set_options",
     "jrlqp_get_options", "jrlqp_solve_batch_device", "jrlqp_solve_batch_host", "jrlqp_get_kernel_info",
     "jrlqp_set_stage_c", "jrlqp_launch_count", "jrlqp_last_error", "jrlqp_measure_fp64_tflops",
+    "jrlqp_structured_create", "jrlqp_structured_destroy", "jrlqp_structured_last_error",
+    "jrlqp_structured_llt_device", "jrlqp_structured_llt_host", "jrlqp_structured_solve_device",
+    "jrlqp_structured_solve_host", "jrlqp_structured_get_info",
 ]
 
 _lib = None
@@ -134,6 +137,17 @@ def load_library():
         lib.jrlqp_set_stage_c.argtypes = [C.c_void_p, C.c_int32]
         lib.jrlqp_solve_batch_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
         lib.jrlqp_solve_batch_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
+        lib.jrlqp_structured_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int32]
+        lib.jrlqp_structured_destroy.argtypes = [C.c_void_p]
+        lib.jrlqp_structured_last_error.restype = C.c_char_p
+        lib.jrlqp_structured_last_error.argtypes = [C.c_void_p]
+        lib.jrlqp_structured_get_info.argtypes = [C.c_void_p, C.c_void_p]
+        lib.jrlqp_structured_llt_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        lib.jrlqp_structured_llt_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        lib.jrlqp_structured_solve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                                      C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        lib.jrlqp_structured_solve_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                                    C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]
         _lib = lib
     return _lib
 

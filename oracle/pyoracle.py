@@ -186,3 +186,45 @@ def givens(p, q):
     out = np.zeros(3)
     lib().gi_oracle_givens(C.c_double(p), C.c_double(q), _dp(out))
     return tuple(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# structured decompositions (oracle/decomp_oracle.cpp)
+# ---------------------------------------------------------------------------------------------
+c_lp = C.POINTER(C.c_long)
+
+
+def _desc_args(st):
+    """st: any object with type, sizes, diag_offset, diag_ld, off_offset, off_ld (see
+    jrl_qp_b200.structured.Structure). Returns (ctypes args, keep-alive list)."""
+    size = np.ascontiguousarray(st.sizes, dtype=np.int32)
+    doff = np.ascontiguousarray(st.diag_offset, dtype=np.int64)
+    dld = np.ascontiguousarray(st.diag_ld, dtype=np.int32)
+    ooff = np.ascontiguousarray(st.off_offset, dtype=np.int64)
+    old = np.ascontiguousarray(st.off_ld, dtype=np.int32)
+    keep = [size, doff, dld, ooff, old]
+    args = [C.c_int(int(st.type)), C.c_int(len(size)), _ip(size), doff.ctypes.data_as(c_lp), _ip(dld),
+            ooff.ctypes.data_as(c_lp), _ip(old)]
+    return args, keep
+
+
+def decomp_llt(st, data, nthreads=1):
+    """In-place structured Cholesky of data [B, stride] (float64, C-contiguous). Returns ok [B] (int32)."""
+    assert data.dtype == np.float64 and data.flags.c_contiguous and data.ndim == 2
+    B, stride = data.shape
+    ok = np.zeros(B, dtype=np.int32)
+    args, keep = _desc_args(st)
+    lib().decomp_oracle_llt(*args, _dp(data), C.c_long(stride), C.c_long(B), _ip(ok), C.c_int(nthreads))
+    return ok
+
+
+def decomp_solve(st, data, M, transpose=False, start=0, end=-1, nthreads=1):
+    """In-place L X = M (or L^T X = M) on M [B, ncols, n] (each instance column-major n x ncols, ld n)."""
+    assert data.dtype == np.float64 and data.flags.c_contiguous and data.ndim == 2
+    assert M.dtype == np.float64 and M.flags.c_contiguous and M.ndim == 3
+    B, stride = data.shape
+    ncols, n = M.shape[1], M.shape[2]
+    args, keep = _desc_args(st)
+    lib().decomp_oracle_solve(*args, _dp(data), C.c_long(stride), _dp(M), C.c_int(n), C.c_int(ncols), C.c_long(ncols * n),
+                              C.c_long(B), C.c_int(1 if transpose else 0), C.c_int(start), C.c_int(end), C.c_int(nthreads))
+    return M
