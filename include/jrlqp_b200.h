@@ -182,6 +182,15 @@ int jrlqp_version(void);
  * TFLOP/s (2 flops per FMA), or a negative error. Used by bench.py for the roofline denominator. */
 double jrlqp_measure_fp64_tflops(int32_t device, int32_t repeats);
 
+/* Self-test of the short-latency exact division / square root used on the solver's serial
+ * recurrences (jrl-qp_b200/csrc/fp64_exact.cuh) against the stock IEEE operations, on `samples`
+ * pseudo-random operand pairs with binary exponents in [-exponent_span, exponent_span] and a
+ * reciprocal perturbed by up to rcp_ulps ulps. counts5 (HOST, 5 entries): [0] quotients proven
+ * correctly rounded, [1] proven yet different from x / y (must be 0), [2] unproven (the kernels
+ * then use the stock division), [3] square roots different from sqrt() (must be 0), [4] reciprocal
+ * square-root by-products further than 4 ulp from the true value. */
+int jrlqp_selftest_arith(int32_t device, int64_t samples, uint64_t seed, int32_t exponent_span, int32_t rcp_ulps, uint64_t * counts5);
+
 /* ------------------------------------------------------------------------------------------------
  * Structured Cholesky decompositions (north-star item 4), batched: `batch` matrices that share ONE
  * block structure are factorised / solved by one call, one instance per CTA.

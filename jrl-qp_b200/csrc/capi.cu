@@ -43,8 +43,8 @@ KernelFn pick_kernel(int warps, bool stage)
 struct Layout
 {
   int ldj, ldcs, npad;
-  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_scr, off_C;
-  int off_alist, off_gk, off_iscr, off_stat;
+  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_rinv, off_scr, off_C;
+  int off_alist, off_gk, off_iscr, off_stat, off_eq;
   int total_doubles;
 };
 
@@ -79,6 +79,8 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage)
   o += 2 * np;
   L.off_ldiag = o;
   o += np;
+  L.off_rinv = o;
+  o += np;
   L.off_scr = o;
   o += 16;
   L.off_C = o;
@@ -90,6 +92,8 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage)
   L.off_iscr = o;
   o += 8;
   L.off_stat = o;
+  o += (mc + nb + 7) / 8 + 1;
+  L.off_eq = o;
   o += (mc + nb + 7) / 8 + 1;
   L.total_doubles = o;
   return L;
@@ -123,6 +127,7 @@ struct jrlqp_solver
   int max_smem_optin = 0;
   // device-side scratch
   unsigned long long * d_counters = nullptr; // kMaxChunks counters
+  unsigned long long * d_phase = nullptr; // per-phase cycle counters (debug builds with -DJRLQP_PHASE_TIMING)
   int next_counter = 0;
   // staging for the host entry point
   double *d_G = nullptr, *d_a = nullptr, *d_C = nullptr, *d_bl = nullptr, *d_bu = nullptr, *d_xl = nullptr, *d_xu = nullptr;
@@ -259,6 +264,10 @@ int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds,
   if(rc != JRLQP_OK) return rc;
   CK(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kMaxChunks));
   CK(cudaMemset(s->d_counters, 0, sizeof(unsigned long long) * kMaxChunks));
+#ifdef JRLQP_PHASE_TIMING
+  CK(cudaMalloc(&s->d_phase, sizeof(unsigned long long) * 64));
+  CK(cudaMemset(s->d_phase, 0, sizeof(unsigned long long) * 64));
+#endif
   for(int i = 0; i < kStreams; ++i) CK(cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking));
   return JRLQP_OK;
 }
@@ -267,7 +276,7 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -310,6 +319,18 @@ int jrlqp_get_kernel_info(const jrlqp_solver * s, jrlqp_kernel_info * info)
   info->num_sms = s->num_sms;
   info->stage_c = s->stage ? 1 : 0;
   info->regs_per_thread = s->regs;
+  return JRLQP_OK;
+}
+
+/* Debug builds only (-DJRLQP_PHASE_TIMING): copies and clears the 4 x 16 per-warp, per-phase cycle
+ * counters. Returns JRLQP_ERR_ARG in normal builds. Not declared in the public header. */
+int jrlqp_debug_phase_cycles(jrlqp_solver * s, unsigned long long * out64)
+{
+  if(!s || !out64 || !s->d_phase) return JRLQP_ERR_ARG;
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out64, s->d_phase, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemset(s->d_phase, 0, sizeof(unsigned long long) * 64));
   return JRLQP_OK;
 }
 
@@ -370,6 +391,7 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.n_active = res->n_active;
   p.L = res->L;
   p.counter = counter;
+  p.phase_cycles = s->d_phase;
   p.ldj = s->lay.ldj;
   p.ldcs = s->lay.ldcs;
   p.npad = s->lay.npad;
@@ -384,12 +406,14 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.off_gs = s->lay.off_gs;
   p.off_gcs = s->lay.off_gcs;
   p.off_ldiag = s->lay.off_ldiag;
+  p.off_rinv = s->lay.off_rinv;
   p.off_scr = s->lay.off_scr;
   p.off_C = s->lay.off_C;
   p.off_alist = s->lay.off_alist;
   p.off_gk = s->lay.off_gk;
   p.off_iscr = s->lay.off_iscr;
   p.off_stat = s->lay.off_stat;
+  p.off_eq = s->lay.off_eq;
   long long grid = std::min<long long>((long long)s->occ * s->num_sms, std::max<long long>(pb->batch, 1));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
   s->kernel<<<(unsigned)grid, 32 * s->warps, s->smem_bytes, st>>>(p);

@@ -30,6 +30,7 @@
 // (dot4 / dot32 / fma axpy / Eigen makeGivens): results are bit-identical to the oracle whatever W.
 #pragma once
 
+#include "fp64_exact.cuh"
 #include "gi_params.h"
 
 #include <cuda_runtime.h>
@@ -38,6 +39,32 @@ namespace jrlqp
 {
 
 #define JRLQP_FULL 0xffffffffu
+
+// Optional per-phase cycle accounting (build with -DJRLQP_PHASE_TIMING; scripts/phase_timing.py):
+// every warp adds the cycles it spends in each phase — waits at barriers included — to
+// P.phase_cycles[warp * 16 + phase].
+#ifdef JRLQP_PHASE_TIMING
+#  define PH_DECL     \
+    ph_t = clock64(); \
+    for(int k_ = 0; k_ < 16; ++k_) ph_acc[k_] = 0
+#  define PH_MARK(id)              \
+    do                             \
+    {                              \
+      long long now_ = clock64();  \
+      ph_acc[id] += now_ - ph_t;   \
+      ph_t = now_;                 \
+    } while(0)
+#  define PH_FLUSH                                                                                      \
+    do                                                                                                  \
+    {                                                                                                   \
+      if(lane == 0 && P.phase_cycles)                                                                   \
+        for(int k_ = 0; k_ < 16; ++k_) atomicAdd(P.phase_cycles + warp * 16 + k_, (unsigned long long)ph_acc[k_]); \
+    } while(0)
+#else
+#  define PH_DECL
+#  define PH_MARK(id)
+#  define PH_FLUSH
+#endif
 #define JRLQP_NONE 0x7fffffff
 
 __device__ __forceinline__ double warp_sum32(double acc)
@@ -109,6 +136,59 @@ __device__ __noinline__ double dot4_uniform(int len, const double * __restrict__
   if(k < len) c0 = fma(a[k], b[k], c0);
   if(k + 1 < len) c1 = fma(a[k + 1], b[k + 1], c1);
   if(k + 2 < len) c2 = fma(a[k + 2], b[k + 2], c2);
+  return (c0 + c1) + (c2 + c3);
+}
+
+// dot4(ci, x) for one constraint normal read from global memory / L2 (thread = constraint: every lane
+// walks its own row, so the loads of a chunk are issued together — CH values in flight per thread,
+// as 128-bit loads when the rows are 16-byte aligned — instead of one round trip per 4 values).
+template<bool VEC, int CH>
+__device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const double * xs, int n)
+{
+  double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  int k = 0;
+#pragma unroll 1
+  for(; k + CH - 1 < n; k += CH)
+  {
+    double v[CH];
+    if(VEC)
+    {
+#pragma unroll
+      for(int u = 0; u < CH / 2; ++u)
+      {
+        const double2 t = *reinterpret_cast<const double2 *>(ci + k + 2 * u);
+        v[2 * u] = t.x;
+        v[2 * u + 1] = t.y;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for(int u = 0; u < CH; ++u) v[u] = ci[k + u];
+    }
+#pragma unroll
+    for(int u = 0; u < CH / 4; ++u)
+    {
+      c0 = fma(v[4 * u], xs[k + 4 * u], c0);
+      c1 = fma(v[4 * u + 1], xs[k + 4 * u + 1], c1);
+      c2 = fma(v[4 * u + 2], xs[k + 4 * u + 2], c2);
+      c3 = fma(v[4 * u + 3], xs[k + 4 * u + 3], c3);
+    }
+  }
+  {
+    // remainder (< CH values): loads first, then the FMAs
+    double v[CH];
+#pragma unroll
+    for(int u = 0; u < CH; ++u) v[u] = k + u < n ? ci[k + u] : 0.0;
+#pragma unroll
+    for(int u = 0; u < CH / 4; ++u)
+    {
+      if(k + 4 * u < n) c0 = fma(v[4 * u], xs[k + 4 * u], c0);
+      if(k + 4 * u + 1 < n) c1 = fma(v[4 * u + 1], xs[k + 4 * u + 1], c1);
+      if(k + 4 * u + 2 < n) c2 = fma(v[4 * u + 2], xs[k + 4 * u + 2], c2);
+      if(k + 4 * u + 3 < n) c3 = fma(v[4 * u + 3], xs[k + 4 * u + 3], c3);
+    }
+  }
   return (c0 + c1) + (c2 + c3);
 }
 
@@ -185,22 +265,29 @@ template<int W, bool STAGE_C>
 struct GiCta
 {
   static constexpr int T = 32 * W;
+  static constexpr int CH = W == 1 ? 8 : 16; // values in flight per thread in the constraint scan
+  static constexpr int PF = W == 1 ? 2 : 4; // rotations per chunk when the Givens table is applied
   // ---- immutable per-launch
   const GiParams & P;
   const int tid, lane, warp;
   const int n, mc, nb, m, ldj;
-  double *Jb, *Rp, *xs, *zs, *ds, *rs, *us, *cv, *gc, *gs, *ldiag, *Cs, *scr;
+  double *Jb, *Rp, *xs, *zs, *ds, *rs, *us, *cv, *gc, *gs, *ldiag, *rinv, *Cs, *scr;
   double2 * gcs; // (c, s) rotation table of the Givens sweep
   int * alist;
   int * gk;
   int * iscr;
   signed char * stat;
+  signed char * eqf; // 1 where bl == bu (resp. xl == xu): constraints initActiveSet pre-activates
   // ---- per-problem views
   const double *Cb, *bl, *bu, *xl, *xu;
   long long ldC; // leading dimension of the constraint-normal storage Cb (staged or global)
+  bool cvec; // rows of Cb are 16-byte aligned (128-bit loads allowed)
   // ---- solver state (uniform across threads)
   int q;
   double f;
+#ifdef JRLQP_PHASE_TIMING
+  long long ph_t, ph_acc[16];
+#endif
 
   __device__ GiCta(const GiParams & p, double * smem)
   : P(p), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), n(p.n), mc(p.mc), nb(p.nb), m(p.mc + p.nb), ldj(p.ldj)
@@ -217,12 +304,14 @@ struct GiCta
     gs = smem + p.off_gs;
     gcs = reinterpret_cast<double2 *>(smem + p.off_gcs);
     ldiag = smem + p.off_ldiag;
+    rinv = smem + p.off_rinv;
     scr = smem + p.off_scr;
     Cs = smem + p.off_C;
     alist = reinterpret_cast<int *>(smem + p.off_alist);
     gk = reinterpret_cast<int *>(smem + p.off_gk);
     iscr = reinterpret_cast<int *>(smem + p.off_iscr);
     stat = reinterpret_cast<signed char *>(smem + p.off_stat);
+    eqf = reinterpret_cast<signed char *>(smem + p.off_eq);
   }
 
   __device__ __forceinline__ void sync() const
@@ -327,7 +416,10 @@ struct GiCta
 #pragma unroll 1
       for(int k = 0; k < n; ++k)
       {
-        double yk = __shfl_sync(JRLQP_FULL, pick<W>(y, k >> 5), k & 31) / ldiag[k];
+        const double lk = ldiag[k], vk = __shfl_sync(JRLQP_FULL, pick<W>(y, k >> 5), k & 31);
+        bool okd;
+        double yk = div_rcp(vk, lk, rs[k], okd); // rs[k] = 1 / L(k,k)
+        if(!okd) yk = vk / lk;
 #pragma unroll
         for(int s = 0; s < W; ++s)
         {
@@ -341,7 +433,10 @@ struct GiCta
 #pragma unroll 1
       for(int k = n - 1; k >= 0; --k)
       {
-        double xk = __shfl_sync(JRLQP_FULL, pick<W>(y, k >> 5), k & 31) / ldiag[k];
+        const double lk = ldiag[k], vk = __shfl_sync(JRLQP_FULL, pick<W>(y, k >> 5), k & 31);
+        bool okd;
+        double xk = div_rcp(vk, lk, rs[k], okd);
+        if(!okd) xk = vk / lk;
 #pragma unroll
         for(int s = 0; s < W; ++s)
         {
@@ -371,6 +466,7 @@ struct GiCta
     //     itself, so no synchronisation is needed between threads while it is built.
     {
       const int j = i;
+      const int jc = ic;
       const int jmax = min(n - 1, 32 * warp + 31); // last column handled by this warp
       if(j < n) Jb[j * ldj + j] = rs[j];
 #pragma unroll 1
@@ -380,11 +476,17 @@ struct GiCta
 #pragma unroll 1
         for(int k0 = r + 1; k0 <= jmax; k0 += 4)
         {
-          // accumulator index (k - r - 1) & 3
-          if(k0 <= j) a0 = fma(Jb[k0 * ldj + r], Jb[k0 * ldj + j], a0);
-          if(k0 + 1 <= j) a1 = fma(Jb[(k0 + 1) * ldj + r], Jb[(k0 + 1) * ldj + j], a1);
-          if(k0 + 2 <= j) a2 = fma(Jb[(k0 + 2) * ldj + r], Jb[(k0 + 2) * ldj + j], a2);
-          if(k0 + 3 <= j) a3 = fma(Jb[(k0 + 3) * ldj + r], Jb[(k0 + 3) * ldj + j], a3);
+          // accumulator index (k - r - 1) & 3. Loads are unconditional (rows past j, even past n - 1,
+          // are addressable shared memory) and the accumulation is a select: no divergent branch.
+          const double * Jk = Jb + k0 * ldj;
+          const double t0 = fma(Jk[r], Jk[jc], a0);
+          const double t1 = fma(Jk[ldj + r], Jk[ldj + jc], a1);
+          const double t2 = fma(Jk[2 * ldj + r], Jk[2 * ldj + jc], a2);
+          const double t3 = fma(Jk[3 * ldj + r], Jk[3 * ldj + jc], a3);
+          a0 = k0 <= j ? t0 : a0;
+          a1 = k0 + 1 <= j ? t1 : a1;
+          a2 = k0 + 2 <= j ? t2 : a2;
+          a3 = k0 + 3 <= j ? t3 : a3;
         }
         if(r < j && j < n) Jb[r * ldj + j] = (-((a0 + a1) + (a2 + a3))) * rs[r];
       }
@@ -398,7 +500,11 @@ struct GiCta
       for(int c = 0; c < i; ++c) Jb[i * ldj + c] = 0.0;
     }
     // A_.reset()
-    for(int c = tid; c < m; c += T) stat[c] = ST_INACTIVE;
+    for(int c = tid; c < m; c += T)
+    {
+      stat[c] = ST_INACTIVE;
+      eqf[c] = (c < mc ? (bl[c] == bu[c]) : (xl[c - mc] == xu[c - mc])) ? 1 : 0; // initActiveSet's tests, once
+    }
     q = 0;
     sync();
     return true;
@@ -409,36 +515,28 @@ struct GiCta
   // Also returns the selected constraint's cx so that computeStepLength_ can reuse it (x is
   // unchanged between the two when step 1 was executed; same dot4 => same bits).
   // ------------------------------------------------------------------------------------------
-  __device__ Sel select(double & cx_sel)
+  // TW = number of warps taking part (W: whole CTA, barriers allowed).
+  template<int TW>
+  __device__ __forceinline__ Sel select(double & cx_sel)
   {
+    constexpr int TT = 32 * TW;
+    const int tt = TW == 1 ? lane : tid;
     double best = 0.0;
     double bestcx = 0.0;
     int code = JRLQP_NONE;
     bool bothneg = false;
-    for(int base = 0; base < mc; base += T)
+    for(int base = 0; base < mc; base += TT)
     {
-      int c = base + tid;
+      int c = base + tt;
       bool act = c < mc && stat[c] == ST_INACTIVE;
       if(__ballot_sync(JRLQP_FULL, act) == 0u) continue; // warp-uniform
       const double * ci = Cb + (long long)min(c, mc - 1) * ldC;
-      double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-      int k = 0;
-#pragma unroll 2
-      for(; k + 3 < n; k += 4)
-      {
-        c0 = fma(ci[k], xs[k], c0);
-        c1 = fma(ci[k + 1], xs[k + 1], c1);
-        c2 = fma(ci[k + 2], xs[k + 2], c2);
-        c3 = fma(ci[k + 3], xs[k + 3], c3);
-      }
-      if(k < n) c0 = fma(ci[k], xs[k], c0);
-      if(k + 1 < n) c1 = fma(ci[k + 1], xs[k + 1], c1);
-      if(k + 2 < n) c2 = fma(ci[k + 2], xs[k + 2], c2);
-      double cx = (c0 + c1) + (c2 + c3);
+      const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
+      const double cx = (!STAGE_C && cvec) ? dot4_row<true, CH>(ci, xs, n) : dot4_row<false, CH>(ci, xs, n);
       if(act)
       {
-        double sl = cx - bl[c];
-        double su = bu[c] - cx;
+        double sl = cx - blc;
+        double su = buc - cx;
         if(sl < 0.0 && su < 0.0) bothneg = true;
         if(sl < best)
         {
@@ -454,9 +552,9 @@ struct GiCta
         }
       }
     }
-    for(int base = 0; base < nb; base += T)
+    for(int base = 0; base < nb; base += TT)
     {
-      int c = base + tid;
+      int c = base + tt;
       if(c < nb && stat[mc + c] == ST_INACTIVE)
       {
         double xi = xs[c];
@@ -492,7 +590,7 @@ struct GiCta
       }
     }
     unsigned anyneg = __ballot_sync(JRLQP_FULL, bothneg);
-    if(W > 1)
+    if(TW > 1)
     {
       if(lane == 0)
       {
@@ -507,7 +605,7 @@ struct GiCta
       code = iscr[0];
       int neg = iscr[1];
 #pragma unroll
-      for(int w = 1; w < W; ++w)
+      for(int w = 1; w < TW; ++w)
       {
         double ov = scr[2 + 2 * w];
         int oc = iscr[2 * w];
@@ -551,6 +649,7 @@ struct GiCta
     // stage the selected normal once (coalesced) — it is read by d, c.z and c.x
     if(general && j < n) cv[j] = Cb[(long long)sc.p * ldC + j];
     sync();
+    PH_MARK(2); // fetch of the selected normal
 
     // d, thread = column
     if(general)
@@ -558,7 +657,7 @@ struct GiCta
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const double * Jc = Jb + jc;
       int i = 0;
-#pragma unroll 1
+#pragma unroll 2
       for(; i + 3 < n; i += 4)
       {
         a0 = fma(Jc[i * ldj], cv[i], a0);
@@ -579,13 +678,14 @@ struct GiCta
       if(j < n) ds[j] = sc.st == ST_UPPER_BOUND ? -Jrow[j] : Jrow[j];
     }
     sync();
+    PH_MARK(3); // d
 
     // z, thread = row: z[i] = dot4_{j=q..n-1}(J(i,j), d[j]), accumulator (j-q)&3
     {
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const double * Jr = Jb + jc * ldj;
       int c = q;
-#pragma unroll 1
+#pragma unroll 2
       for(; c + 3 < n; c += 4)
       {
         a0 = fma(Jr[c], ds[c], a0);
@@ -600,13 +700,13 @@ struct GiCta
     }
 
     // the two serial recurrences, concurrently on different warps when W > 1
-    if(warp == 0) back_substitution();
-    if(warp == (W > 1 ? 1 : 0)) givens_recurrence();
     sync();
+    PH_MARK(4); // z
   }
 
   // r = R^-1 d(0:q): column-oriented back substitution with true division, one warp, rows over
-  // the lanes (W slots).
+  // the lanes (W slots). The quotient w_k / R(k,k) comes from the reciprocal kept in rinv[k]
+  // (div_rcp: 3 dependent FMAs, proven correctly rounded, stock division otherwise).
   __device__ __forceinline__ void back_substitution()
   {
     double w[W], rr[W];
@@ -616,20 +716,47 @@ struct GiCta
       w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
       rr[s] = 0.0;
     }
+    // Fast pass: every quotient from the stored reciprocal, its proof accumulated in `allok` instead of
+    // being branched on (the branch would sit on the dependent chain). In the rare case one proof is
+    // declined the pass is redone with the stock division.
+    bool allok = true;
 #pragma unroll 1
-    for(int k = q - 1; k >= 0; --k)
+    for(int pass = 0; pass < 2; ++pass)
     {
-      const double * Rk = Rp + colR(k);
-      double rk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31) / Rk[k];
-#pragma unroll
-      for(int s = 0; s < W; ++s)
+      if(pass == 1)
       {
-        if(32 * s >= k + 1) continue; // slot entirely above row k
-        int r = lane + 32 * s;
-        if(r == k)
-          rr[s] = rk;
-        else if(r < k)
-          w[s] = fma(-rk, Rk[r], w[s]);
+        if(allok) break;
+#pragma unroll
+        for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
+      }
+#pragma unroll 1
+      for(int k = q - 1; k >= 0; --k)
+      {
+        const double * Rk = Rp + colR(k);
+        const double rkk = Rk[k], ri = rinv[k];
+        double col[W];
+#pragma unroll
+        for(int s = 0; s < W; ++s) col[s] = Rk[min(lane + 32 * s, k)];
+        const double wk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31);
+        double rk;
+        if(pass == 0)
+        {
+          bool ok;
+          rk = div_rcp(wk, rkk, ri, ok);
+          allok = allok && ok;
+        }
+        else
+          rk = wk / rkk;
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          if(32 * s >= k + 1) continue; // slot entirely above row k
+          int r = lane + 32 * s;
+          if(r == k)
+            rr[s] = rk;
+          else if(r < k)
+            w[s] = fma(-rk, col[s], w[s]);
+        }
       }
     }
 #pragma unroll
@@ -643,36 +770,79 @@ struct GiCta
   // does not feed the recurrence: it is evaluated afterwards, one rotation per lane.
   __device__ __forceinline__ void givens_recurrence()
   {
-    double rho = ds[n - 1];
+    // Latency of one link is what matters here. Per link, Eigen's makeGivens needs t = num / den,
+    // u = sqrt(1 + t^2), r = den u, with den = rho (the running value) in the common case
+    // |rho| >= |p|. The stock division and square root chain ~20 dependent FP64 operations; here
+    //  * a reciprocal of rho is carried along the recurrence (rr0 = |1/rho| * y1, y1 ~ 1/sqrt(1+t^2)
+    //    being a by-product of the square root), so that t costs 2 dependent FMAs after rho is known
+    //    (div_rcp with the product q0 = p * rr0 issued one link ahead), and is PROVEN to be the
+    //    correctly rounded quotient by an exact remainder test off the chain (see fp64_exact.cuh);
+    //  * every other case (|d[i]| > |rho|, a zero operand, proof declined) leaves the straight-line
+    //    fast path through one branch and is evaluated with precomputed 1 / d[i] or literally.
+    double * rpv = reinterpret_cast<double *>(gcs); // 1 / d[i]; gcs is only written after the chain
 #pragma unroll 1
-    for(int i = n - 2; i >= q; --i)
+    for(int i = q + lane; i <= n - 1; i += 32) rpv[i] = 1.0 / ds[i];
+    __syncwarp();
+    double rho = ds[n - 1];
+    double rrR = rpv[n - 1]; // reciprocal of rho, refined
+    double rrE = rrR; // reciprocal of rho available before rho itself (feeds q0 and the correction)
+    int i = n - 2;
+    double p = ds[max(i, 0)];
+    double q0s = p * rrE; // first product of the quotient p / rho, issued ahead
+#pragma unroll 2
+    for(; i >= q; --i)
     {
-      const double p = ds[i];
-      double a, u = 1.0, r;
-      int kind;
-      if(rho == 0.0)
+      const double pn = ds[max(i - 1, 0)]; // operand of the next link
+      // ---- fast path: t = p / rho, straight line
+      const double e3 = fma(-rho, q0s, p);
+      double a = fma(e3, rrE, q0s);
+      const double e2 = fma(-rho, a, p); // exact remainder (proof)
+      double y1;
+      const double us = sqrt_rsqrt(fma(a, a, 1.0), y1);
+      double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
+      double rr0 = fabs(rrR) * y1; // ~ 1 / r, known before r
+      double rrn = fma(rr0, fma(-r, rr0, 1.0), rr0);
+      double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
+      int kind = 3;
+      // proof that a == RN(p / rho): |e2| < |rho| ulp(a) / 2, a not a power of two, nothing near underflow
+      const int ahi = __double2hiint(a);
+      const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
+      const double tol = fabs(rho) * hu;
+      const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
+      const bool fast = fabs(e2) < tol && tol > 1e-270 && !pow2 && fabs(p) <= fabs(rho) && p != 0.0;
+      if(!fast)
       {
-        kind = 0;
-        a = p;
-        r = fabs(p);
-      }
-      else if(p == 0.0)
-      {
-        kind = 1;
-        a = rho;
-        r = fabs(rho);
-      }
-      else
-      {
-        // |p| > |rho|: t = rho/p, sign and r from p; otherwise t = p/rho, sign and r from rho
-        const bool pg = fabs(p) > fabs(rho);
-        kind = pg ? 2 : 3;
-        const double num = pg ? rho : p;
-        const double den = pg ? p : rho;
-        a = num / den;
-        u = sqrt(fma(a, a, 1.0));
-        if(den < 0.0) u = -u;
-        r = den * u;
+        const double rp = rpv[i];
+        if(rho == 0.0)
+        {
+          kind = 0;
+          a = p;
+          u = 1.0;
+          r = fabs(p);
+          rr0 = fabs(rp);
+        }
+        else if(p == 0.0)
+        {
+          kind = 1;
+          a = rho;
+          u = 1.0;
+          r = fabs(rho);
+          rr0 = fabs(rrR);
+        }
+        else
+        {
+          const bool pg = fabs(p) > fabs(rho);
+          kind = pg ? 2 : 3;
+          const double num = pg ? rho : p, den = pg ? p : rho;
+          bool ok = false;
+          if(pg) a = div_rcp(num, den, rp, ok); // 1 / p was precomputed
+          if(!ok) a = num / den;
+          const double uu = sqrt(fma(a, a, 1.0));
+          u = den < 0.0 ? -uu : uu;
+          r = den * u;
+          rr0 = 1.0 / r;
+        }
+        rrn = rr0;
       }
       if(lane == 0)
       {
@@ -682,7 +852,12 @@ struct GiCta
         gk[i] = kind;
       }
       rho = r;
+      rrR = rrn;
+      rrE = rr0;
+      p = pn;
+      q0s = pn * rr0;
     }
+    if(lane == 0) scr[11] = rrR; // ~ 1 / rho: reciprocal of the new diagonal entry of R
     if(lane == 0) scr[10] = rho;
     __syncwarp();
 #pragma unroll 1
@@ -823,19 +998,30 @@ struct GiCta
     }
   }
 
-  // x += t z ; f += t (n+.z) (t/2 + u[q]) ; u(0:q) -= t r ; u[q] += t
-  __device__ void take_step(double t, double nz, bool primal)
+  // x += t z ; f += t (n+.z) (t/2 + u[q]) ; u(0:q) -= t r ; u[q] += t   — by warp 0 alone (rows and
+  // multipliers over its lanes, W slots), right after step_length on the same warp.
+  __device__ __forceinline__ void take_step(double t, double nz, bool primal)
   {
     const double uq = us[q];
-    sync(); // every warp has finished reading x, u, z, r in step_length before they are updated
+    __syncwarp(); // every lane has finished reading x, u, z, r in step_length
     if(primal)
     {
-      if(tid < n) xs[tid] = fma(t, zs[tid], xs[tid]);
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        const int r = lane + 32 * s;
+        if(r < n) xs[r] = fma(t, zs[r], xs[r]);
+      }
       f += (t * nz) * (0.5 * t + uq);
     }
-    if(tid < q) us[tid] = fma(-t, rs[tid], us[tid]);
-    sync(); // everybody has read u[q]
-    if(tid == 0) us[q] = uq + t;
+#pragma unroll
+    for(int s = 0; s < W; ++s)
+    {
+      const int k = lane + 32 * s;
+      if(k < q) us[k] = fma(-t, rs[k], us[k]);
+    }
+    if(lane == 0) us[q] = uq + t;
+    __syncwarp();
   }
 
   // ------------------------------------------------------------------------------------------
@@ -843,22 +1029,68 @@ struct GiCta
   // apply the rotation table built by givens_recurrence(), thread = row of J, the rotated value
   // of column i+1 is carried in a register from one rotation to the next.
   // ------------------------------------------------------------------------------------------
-  __device__ void add_constraint(Sel sc)
+  __device__ void add_constraint()
   {
-    if(tid == 0)
-    {
-      alist[q] = sc.p;
-      stat[sc.p] = (signed char)sc.st;
-    }
-    q += 1;
+    q += 1; // the active list / status entry was written by warp 0 (solve())
     if(tid < n)
     {
       double * Jr = Jb + tid * ldj;
       if(q - 1 <= n - 2)
       {
         double y = Jr[n - 1];
-#pragma unroll 2
-        for(int i = n - 2; i >= q - 1; --i)
+        int i = n - 2;
+        const int lo = q - 1;
+        // chunks of PF rotations; the operands of the next chunk are loaded BEFORE the results of the
+        // current one are stored (the compiler cannot move a load above a store it cannot disambiguate)
+        double xv[PF];
+        double2 cv4[PF];
+        if(i - (PF - 1) >= lo)
+        {
+#pragma unroll
+          for(int u = 0; u < PF; ++u)
+          {
+            xv[u] = Jr[i - u];
+            cv4[u] = gcs[i - u];
+          }
+        }
+#pragma unroll 1
+        while(i - (PF - 1) >= lo)
+        {
+          double xn[PF];
+          double2 cn[PF];
+          const bool more = i - (2 * PF - 1) >= lo;
+          if(more)
+          {
+#pragma unroll
+            for(int u = 0; u < PF; ++u)
+            {
+              xn[u] = Jr[i - PF - u];
+              cn[u] = gcs[i - PF - u];
+            }
+          }
+          double o[PF];
+#pragma unroll
+          for(int u = 0; u < PF; ++u)
+          {
+            const double c = cv4[u].x, sn = cv4[u].y, xi = xv[u];
+            o[u] = fma(c, y, sn * xi);
+            y = fma(c, xi, -(sn * y));
+          }
+#pragma unroll
+          for(int u = 0; u < PF; ++u) Jr[i - u + 1] = o[u];
+          i -= PF;
+          if(more)
+          {
+#pragma unroll
+            for(int u = 0; u < PF; ++u)
+            {
+              xv[u] = xn[u];
+              cv4[u] = cn[u];
+            }
+          }
+        }
+#pragma unroll 1
+        for(; i >= lo; --i)
         {
           const double2 cs2 = gcs[i];
           const double c = cs2.x, sn = cs2.y;
@@ -870,6 +1102,7 @@ struct GiCta
       }
       // R(0:q, q-1) = d(0:q), with d[q-1] = rho
       if(tid < q) Rp[colR(q - 1) + tid] = tid == q - 1 ? scr[10] : ds[tid];
+      if(tid == q - 1) rinv[tid] = scr[11];
     }
     sync();
   }
@@ -920,7 +1153,11 @@ struct GiCta
         double c, sn, r;
         make_givens(Ri1[i], Ri1[i + 1], c, sn, r);
         __syncwarp();
-        if(lane == 0) Ri[i] = r;
+        if(lane == 0)
+        {
+          Ri[i] = r;
+          rinv[i] = 1.0 / r;
+        }
         // rows i, i+1 of columns i+2 .. q (lane = column)
 #pragma unroll
         for(int s = 0; s < W; ++s)
@@ -978,8 +1215,12 @@ struct GiCta
       Cb = P.C + b * P.sC;
       ldC = P.ldc;
     }
+    cvec = ((reinterpret_cast<unsigned long long>(Cb) & 15ull) == 0ull) && ((ldC & 1) == 0);
 
-    if(!init(b))
+    PH_DECL;
+    const bool init_ok = init(b);
+    PH_MARK(0);
+    if(!init_ok)
     {
       write_failure(b, TS_NON_POS_HESSIAN);
       return;
@@ -989,9 +1230,13 @@ struct GiCta
     int it = 0;
     int cursor = 0; // next constraint / bound to test for pre-activation; m when that phase is over
     bool skip = false;
+    bool have_sel = false; // the constraint of this iteration was already selected at the end of the previous one
     Sel sc{-1, ST_INACTIVE};
     double cx_sel = 0.0;
     const double big = P.big_bnd;
+    // Decisions are taken by warp 0 (while warp 1 runs the Givens recurrence) and published here.
+    int * dec = iscr + 2 * W; // [0] add, [1] l, [2] status on break (-1: none), [5] select the next constraint now
+    double * decd = scr + 13; // [0] f
 #pragma unroll 1
     for(;;)
     {
@@ -1000,7 +1245,7 @@ struct GiCta
       while(cursor < m)
       {
         const int c = cursor++;
-        if(c < mc ? (bl[c] == bu[c]) : (xl[c - mc] == xu[c - mc]))
+        if(eqf[c])
         {
           sc = {c, c < mc ? ST_EQUALITY : ST_FIXED};
           pre = true;
@@ -1012,7 +1257,9 @@ struct GiCta
         if(it >= P.max_iter) break; // MAX_ITER_REACHED
         if(!skip)
         {
-          sc = select(cx_sel);
+          PH_MARK(11);
+          if(!have_sel) sc = select<W>(cx_sel);
+          PH_MARK(1);
           if(sc.st == ST_INACTIVE)
           {
             status = TS_SUCCESS;
@@ -1020,37 +1267,110 @@ struct GiCta
           }
         }
       }
+      // will the step after this one need a fresh selection (i.e. is the pre-activation phase over)?
+      bool more_pre = false;
+      for(int c = cursor; c < m; ++c)
+        if(eqf[c])
+        {
+          more_pre = true;
+          break;
+        }
       if(pre || !skip)
       {
         if(tid == 0) us[q] = 0.0; // published by the barriers of compute_step
       }
+      PH_MARK(11);
       compute_step(sc);
-      double t1, t2, nz;
-      int l;
-      bool zpos;
-      step_length(sc, !pre && !skip, cx_sel, t1, t2, l, nz, zpos);
-      double t;
-      bool primal = true, add = true;
-      if(pre)
-        t = zpos ? t2 : 0.0; // exact step onto the constraint (src/GoldfarbIdnaniSolver.cpp:307-322)
+      // ---- warp 0: r = R^-1 d1, step length, the step itself and, when a constraint is added, the
+      //      bookkeeping of the add;
+      //      warp 1 (warp 0 when W == 1): the Givens recurrence of the add that may follow.
+      if(warp == 0)
+      {
+        back_substitution();
+        PH_MARK(5);
+        double t1, t2, nz;
+        int l;
+        bool zpos;
+        step_length(sc, !pre && !skip, cx_sel, t1, t2, l, nz, zpos);
+        PH_MARK(7);
+        double t;
+        bool primal = true, add = true;
+        int brk = -1;
+        if(pre)
+          t = zpos ? t2 : 0.0; // exact step onto the constraint (src/GoldfarbIdnaniSolver.cpp:307-322)
+        else
+        {
+          t = t2 < t1 ? t2 : t1; // std::min(t1, t2)
+          if(t >= big)
+            brk = TS_INFEASIBLE;
+          else if(t2 >= big)
+            primal = add = false; // dual-only step, then drop
+          else
+            add = t == t2; // full step -> add ; partial step -> drop
+        }
+        int nvalid = 0;
+        if(brk < 0)
+        {
+          take_step(t, nz, primal);
+          PH_MARK(8);
+          if(add)
+          {
+            // DualSolver::addConstraint bookkeeping (src/DualSolver.cpp:231-235)
+            if(lane == 0)
+            {
+              alist[q] = sc.p;
+              stat[sc.p] = (signed char)sc.st;
+            }
+            nvalid = (!more_pre && (pre || it + 1 < P.max_iter)) ? 1 : 0;
+          }
+        }
+        if(lane == 0)
+        {
+          dec[0] = add;
+          dec[1] = l;
+          dec[2] = brk;
+          dec[5] = nvalid;
+          decd[0] = f;
+        }
+      }
+      if(warp == (W > 1 ? 1 : 0))
+      {
+        givens_recurrence();
+        PH_MARK(6);
+      }
+      sync();
+      PH_MARK(11);
+      const bool add = dec[0] != 0;
+      const int l = dec[1];
+      const int brk = dec[2];
+      f = decd[0];
+      if(brk >= 0)
+      {
+        status = brk;
+        break;
+      }
+      have_sel = dec[5] != 0;
+      if(add)
+      {
+        // x and the active set are final: the next violated constraint can be selected now, by the
+        // whole CTA, before the rotations are applied (they do not touch x)
+        Sel nxt{-1, ST_INACTIVE};
+        double cxn = 0.0;
+        if(have_sel) nxt = select<W>(cxn);
+        PH_MARK(1);
+        add_constraint();
+        PH_MARK(9);
+        if(have_sel)
+        {
+          sc = nxt;
+          cx_sel = cxn;
+        }
+      }
       else
       {
-        t = t2 < t1 ? t2 : t1; // std::min(t1, t2)
-        if(t >= big)
-        {
-          status = TS_INFEASIBLE;
-          break;
-        }
-        if(t2 >= big)
-          primal = add = false; // dual-only step, then drop
-        else
-          add = t == t2; // full step -> add ; partial step -> drop
-      }
-      take_step(t, nz, primal);
-      if(add)
-        add_constraint(sc);
-      else
         remove_constraint(l);
+        PH_MARK(10);
+      }
       if(!pre)
       {
         skip = !add;
@@ -1058,7 +1378,10 @@ struct GiCta
       }
     }
     sync();
+    PH_MARK(11);
     write_result(b, status, it);
+    PH_MARK(12);
+    PH_FLUSH;
   }
 
   __device__ void write_result(long long b, int status, int it)
@@ -1123,7 +1446,7 @@ struct GiCta
 // Persistent kernel: grid = resident CTAs of the whole GPU; every CTA pulls the next problem index
 // from an atomic ticket counter, which absorbs the divergent iteration counts across QPs.
 template<int W, bool STAGE_C>
-__global__ void __launch_bounds__(32 * W, (W == 1 ? 24 : (W == 2 ? 6 : 1))) gi_dense_cta_kernel(const GiParams p)
+__global__ void __launch_bounds__(32 * W, (W == 1 ? 16 : (W == 2 ? 6 : 1))) gi_dense_cta_kernel(const GiParams p)
 {
   extern __shared__ __align__(16) double smem[];
   GiCta<W, STAGE_C> cta(p, smem);

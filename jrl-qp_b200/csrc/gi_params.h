@@ -64,12 +64,13 @@ struct GiParams
   double * L;
   // persistent work queue
   unsigned long long * counter;
+  unsigned long long * phase_cycles; // [4 warps][16 phases], only with -DJRLQP_PHASE_TIMING (else null)
   // shared-memory layout (computed on the host, in doubles unless noted)
   int ldj; // leading dimension of the row-major J/L buffer (odd => conflict-free row-strided access)
   int ldcs; // leading dimension of the staged C (odd), if staged
   int npad; // threads per CTA (>= n)
-  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_scr, off_C; // offsets in doubles
-  int off_alist, off_gk, off_iscr, off_stat; // offsets in doubles of the int / int8 arrays
+  int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_rinv, off_scr, off_C; // offsets in doubles
+  int off_alist, off_gk, off_iscr, off_stat, off_eq; // offsets in doubles of the int / int8 arrays
 };
 
 } // namespace jrlqp

@@ -108,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "jrlqp_set_stage_c", "jrlqp_launch_count", "jrlqp_last_error", "jrlqp_measure_fp64_tflops",
     "jrlqp_structured_create", "jrlqp_structured_destroy", "jrlqp_structured_last_error",
     "jrlqp_structured_llt_device", "jrlqp_structured_llt_host", "jrlqp_structured_solve_device",
-    "jrlqp_structured_solve_host", "jrlqp_structured_get_info",
+    "jrlqp_structured_solve_host", "jrlqp_structured_get_info", "jrlqp_selftest_arith",
 ]
 
 _lib = None
@@ -150,6 +150,17 @@ def load_library():
                                                     C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]
         _lib = lib
     return _lib
+
+
+def selftest_arith(samples=1 << 24, seed=1, exponent_span=30, rcp_ulps=3, device=0):
+    """counts of jrlqp_selftest_arith: (proven, proven_but_wrong, unproven, sqrt_mismatch, rsqrt_far)."""
+    lib = load_library()
+    out = (C.c_uint64 * 5)()
+    rc = lib.jrlqp_selftest_arith(C.c_int32(device), C.c_int64(samples), C.c_uint64(seed), C.c_int32(exponent_span),
+                                  C.c_int32(rcp_ulps), out)
+    if rc != 0:
+        raise RuntimeError(f"jrlqp_selftest_arith failed ({rc})")
+    return tuple(int(v) for v in out)
 
 
 def launch_count():

@@ -293,3 +293,14 @@ def test_headline_config_full_size_properties():
     sub = P.ProblemBatch(pb.G[idx], pb.a[idx], pb.C[idx], pb.bl[idx], pb.bu[idx], pb.xl[idx], pb.xu[idx])
     ref = _oracle(sub)
     assert_parity({k: v[idx] for k, v in g.items() if isinstance(v, np.ndarray)}, ref)
+
+
+@pytest.mark.parametrize("span,ulps", [(0, 0), (30, 3), (300, 3), (30, 200), (600, 1)])
+def test_exact_arithmetic_primitives(span, ulps):
+    """fp64_exact.cuh: a quotient that div_rcp declares proven IS x / y bit for bit, whatever reciprocal
+    approximation it was given; the restated square-root sequence IS sqrt() bit for bit on [1, 2]."""
+    proven, wrong, unproven, sqrt_bad, rsqrt_far = S.selftest_arith(1 << 26, seed=span * 1000 + ulps, exponent_span=span, rcp_ulps=ulps)
+    assert wrong == 0 and sqrt_bad == 0 and rsqrt_far == 0
+    total = proven + unproven
+    if span <= 30 and ulps <= 3:  # beyond +-400 binades of range the proof is declined by design
+        assert unproven <= 1e-3 * total  # the stock-division fallback is rare
