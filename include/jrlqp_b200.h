@@ -157,6 +157,22 @@ int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const j
  * of the batch (>= 0) or a negative JRLQP_ERR_*. */
 int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res);
 
+/* experimental::GoldfarbIdnaniSolver::solve(G, a, C, bl, bu, xl, xu, as)
+ * (include/jrl-qp/experimental/GoldfarbIdnaniSolver.h:27-34, src/experimental/GoldfarbIdnaniSolver.cpp:21-111,
+ * 306-486), the warm-start capable solver, batched: the guessed active set pb->as_in (nullable) is
+ * honoured when options.warm_start != 0 — equalities of the data always are —, the corresponding
+ * normals are factorised at once (B = L^-1 N = Q R, J = L^-T Q), constraints that come out with a
+ * negative multiplier are dropped, and the usual iteration follows; `iterations` counts those drops
+ * plus the iterations, so a correct guess gives 0 (tests/GoldfarbIdnaniSolverTest.cpp:176-181).
+ * The reference's "as empty => reuse the active set of the previous call" is the caller passing the
+ * previous result's active_set back as as_in. Guesses that cannot apply are ignored as in the
+ * reference (FIXED on distinct bounds, a side whose bound is infinite); statuses of the wrong kind
+ * (a bound status on a general constraint or vice versa), on which the reference asserts, are ignored.
+ * JRLQP_OVERCONSTRAINED_PROBLEM is reported per instance when more than n equalities are given.
+ * Needs n (n - 1) / 2 more doubles of shared memory than the cold kernel (n <= ~100). */
+int jrlqp_solve_batch_warm_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream);
+int jrlqp_solve_batch_warm_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res);
+
 /* Introspection used by the benchmark harness. */
 typedef struct jrlqp_kernel_info
 {

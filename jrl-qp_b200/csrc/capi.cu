@@ -23,6 +23,23 @@ constexpr int kMaxChunks = 64;
 
 using KernelFn = void (*)(const GiParams);
 
+KernelFn pick_warm_kernel(int warps)
+{
+  switch(warps)
+  {
+    case 1:
+      return gi_dense_cta_kernel<1, false, true>;
+    case 2:
+      return gi_dense_cta_kernel<2, false, true>;
+    case 3:
+      return gi_dense_cta_kernel<3, false, true>;
+    case 4:
+      return gi_dense_cta_kernel<4, false, true>;
+    default:
+      return nullptr;
+  }
+}
+
 KernelFn pick_kernel(int warps, bool stage)
 {
   switch(warps)
@@ -45,10 +62,11 @@ struct Layout
   int ldj, ldcs, npad;
   int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_rinv, off_scr, off_C;
   int off_alist, off_gk, off_iscr, off_stat, off_eq;
+  int off_V, off_bact, off_hco, off_alpha;
   int total_doubles;
 };
 
-Layout make_layout(int n, int mc, int nb, int warps, bool stage)
+Layout make_layout(int n, int mc, int nb, int warps, bool stage, bool warm = false)
 {
   Layout L{};
   L.ldj = n | 1;
@@ -95,6 +113,18 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage)
   o += (mc + nb + 7) / 8 + 1;
   L.off_eq = o;
   o += (mc + nb + 7) / 8 + 1;
+  L.off_V = L.off_bact = L.off_hco = L.off_alpha = o;
+  if(warm)
+  {
+    L.off_V = o;
+    o += n * (n - 1) / 2 + 1;
+    L.off_bact = o;
+    o += np;
+    L.off_hco = o;
+    o += np;
+    L.off_alpha = o;
+    o += np;
+  }
   L.total_doubles = o;
   return L;
 }
@@ -122,6 +152,12 @@ struct jrlqp_solver
   KernelFn kernel = nullptr;
   int smem_bytes = 0;
   int occ = 0;
+  // warm-start (experimental solver) kernel: own shared-memory layout, configured on first use
+  Layout wlay{};
+  KernelFn wkernel = nullptr;
+  int wsmem_bytes = 0;
+  int wocc = 0;
+  signed char * d_as = nullptr; // staging of as_in for the host entry point
   int num_sms = 0;
   int regs = 0;
   int max_smem_optin = 0;
@@ -276,7 +312,7 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -356,8 +392,16 @@ static int validate(const jrlqp_solver * s, const jrlqp_problem * pb, const jrlq
   return JRLQP_OK;
 }
 
-static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter)
+static int configure_warm(jrlqp_solver * s);
+
+static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter, bool warm = false)
 {
+  if(warm)
+  {
+    int rc = configure_warm(s);
+    if(rc != JRLQP_OK) return rc;
+  }
+  const Layout & lay = warm ? s->wlay : s->lay;
   GiParams p{};
   p.n = s->n;
   p.mc = s->mc;
@@ -381,6 +425,9 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.sxl = pb->xl_stride;
   p.xu = pb->xu;
   p.sxu = pb->xu_stride;
+  p.as_in = warm ? reinterpret_cast<const signed char *>(pb->as_in) : nullptr;
+  p.s_as = pb->as_stride;
+  p.warm_start = warm ? s->opt.warm_start : 0;
   p.x = res->x;
   p.u = res->u;
   p.f = res->f;
@@ -392,34 +439,78 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.L = res->L;
   p.counter = counter;
   p.phase_cycles = s->d_phase;
-  p.ldj = s->lay.ldj;
-  p.ldcs = s->lay.ldcs;
-  p.npad = s->lay.npad;
-  p.off_R = s->lay.off_R;
-  p.off_x = s->lay.off_x;
-  p.off_z = s->lay.off_z;
-  p.off_d = s->lay.off_d;
-  p.off_r = s->lay.off_r;
-  p.off_u = s->lay.off_u;
-  p.off_cv = s->lay.off_cv;
-  p.off_gc = s->lay.off_gc;
-  p.off_gs = s->lay.off_gs;
-  p.off_gcs = s->lay.off_gcs;
-  p.off_ldiag = s->lay.off_ldiag;
-  p.off_rinv = s->lay.off_rinv;
-  p.off_scr = s->lay.off_scr;
-  p.off_C = s->lay.off_C;
-  p.off_alist = s->lay.off_alist;
-  p.off_gk = s->lay.off_gk;
-  p.off_iscr = s->lay.off_iscr;
-  p.off_stat = s->lay.off_stat;
-  p.off_eq = s->lay.off_eq;
-  long long grid = std::min<long long>((long long)s->occ * s->num_sms, std::max<long long>(pb->batch, 1));
+  p.ldj = lay.ldj;
+  p.ldcs = lay.ldcs;
+  p.npad = lay.npad;
+  p.off_R = lay.off_R;
+  p.off_x = lay.off_x;
+  p.off_z = lay.off_z;
+  p.off_d = lay.off_d;
+  p.off_r = lay.off_r;
+  p.off_u = lay.off_u;
+  p.off_cv = lay.off_cv;
+  p.off_gc = lay.off_gc;
+  p.off_gs = lay.off_gs;
+  p.off_gcs = lay.off_gcs;
+  p.off_ldiag = lay.off_ldiag;
+  p.off_rinv = lay.off_rinv;
+  p.off_scr = lay.off_scr;
+  p.off_C = lay.off_C;
+  p.off_alist = lay.off_alist;
+  p.off_gk = lay.off_gk;
+  p.off_iscr = lay.off_iscr;
+  p.off_stat = lay.off_stat;
+  p.off_eq = lay.off_eq;
+  p.off_V = lay.off_V;
+  p.off_bact = lay.off_bact;
+  p.off_hco = lay.off_hco;
+  p.off_alpha = lay.off_alpha;
+  const int occ = warm ? s->wocc : s->occ;
+  long long grid = std::min<long long>((long long)occ * s->num_sms, std::max<long long>(pb->batch, 1));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-  s->kernel<<<(unsigned)grid, 32 * s->warps, s->smem_bytes, st>>>(p);
+  if(warm)
+    s->wkernel<<<(unsigned)grid, 32 * s->warps, s->wsmem_bytes, st>>>(p);
+  else
+    s->kernel<<<(unsigned)grid, 32 * s->warps, s->smem_bytes, st>>>(p);
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return JRLQP_OK;
+}
+
+static int configure_warm(jrlqp_solver * s)
+{
+  if(s->wkernel) return JRLQP_OK;
+  Layout lay = make_layout(s->n, s->mc, s->nb, s->warps, false, true);
+  const int smem = lay.total_doubles * 8;
+  KernelFn fn = pick_warm_kernel(s->warps);
+  if(!fn || smem > s->max_smem_optin)
+  {
+    s->err = "warm start: problem does not fit in shared memory (n too large; the Householder vectors need n (n - 1) / 2 more doubles)";
+    return JRLQP_ERR_ARG;
+  }
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * s->warps, smem));
+  if(occ < 1)
+  {
+    s->err = "warm start kernel cannot be made resident";
+    return JRLQP_ERR_ARG;
+  }
+  s->wlay = lay;
+  s->wsmem_bytes = smem;
+  s->wocc = occ;
+  s->wkernel = fn;
+  return JRLQP_OK;
+}
+
+int jrlqp_solve_batch_warm_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream)
+{
+  int rc = validate(s, pb, res);
+  if(rc != JRLQP_OK) return rc;
+  if(pb->batch == 0) return JRLQP_OK;
+  CK(cudaSetDevice(s->device));
+  unsigned long long * counter = s->d_counters + (s->next_counter++ % kMaxChunks);
+  return launch(s, pb, res, (cudaStream_t)stream, counter, true);
 }
 
 int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream)
@@ -482,7 +573,7 @@ static cudaError_t h2d(double * dst, const double * src, long long stride, long 
   return cudaSuccess;
 }
 
-int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res)
+static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, bool warm)
 {
   int rc = validate(s, pb, res);
   if(rc != JRLQP_OK) return rc;
@@ -543,7 +634,19 @@ int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrl
     dr.active_list = res->active_list ? s->d_alist + b0 * n : nullptr;
     dr.n_active = res->n_active ? s->d_nact + b0 : nullptr;
     dr.L = res->L ? s->d_L + b0 * n * n : nullptr;
-    rc = launch(s, &dp, &dr, st, s->d_counters + (c % kMaxChunks));
+    if(warm && pb->as_in)
+    {
+      if(!s->d_as) CK(cudaMalloc(&s->d_as, std::max<long long>(std::max<long long>(s->capacity, 1) * m, 1)));
+      const long long cnt_as = pb->as_stride == 0 ? 1 : cnt;
+      signed char * das = s->d_as + b0 * m;
+      if(pb->as_stride == m || cnt_as == 1)
+        CK(cudaMemcpyAsync(das, pb->as_in + b0 * pb->as_stride, (size_t)(cnt_as * m), cudaMemcpyHostToDevice, st));
+      else
+        CK(cudaMemcpy2DAsync(das, (size_t)m, pb->as_in + b0 * pb->as_stride, (size_t)pb->as_stride, (size_t)m, (size_t)cnt_as, cudaMemcpyHostToDevice, st));
+      dp.as_in = reinterpret_cast<const int8_t *>(das);
+      dp.as_stride = pb->as_stride == 0 ? 0 : m;
+    }
+    rc = launch(s, &dp, &dr, st, s->d_counters + (c % kMaxChunks), warm);
     if(rc != JRLQP_OK) return rc;
     CK(cudaMemcpyAsync(res->x + b0 * n, dr.x, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, st));
     if(res->u && m) CK(cudaMemcpyAsync(res->u + b0 * m, dr.u, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, st));
@@ -570,6 +673,16 @@ int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrl
     for(long long b = 0; b < B; ++b) worst = std::max(worst, hs[(size_t)b]);
   }
   return worst;
+}
+
+int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res)
+{
+  return solve_batch_host_impl(s, pb, res, false);
+}
+
+int jrlqp_solve_batch_warm_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res)
+{
+  return solve_batch_host_impl(s, pb, res, true);
 }
 
 } // extern "C"

@@ -261,7 +261,7 @@ __device__ __noinline__ Sel select_sequential(int n,
   return sel;
 }
 
-template<int W, bool STAGE_C>
+template<int W, bool STAGE_C, bool WARM = false>
 struct GiCta
 {
   static constexpr int T = 32 * W;
@@ -277,6 +277,7 @@ struct GiCta
   int * gk;
   int * iscr;
   signed char * stat;
+  double *Vp, *bact, *hco, *alp; // warm start: Householder vectors (packed), b_act, tau, alpha = J^T a
   signed char * eqf; // 1 where bl == bu (resp. xl == xu): constraints initActiveSet pre-activates
   // ---- per-problem views
   const double *Cb, *bl, *bu, *xl, *xu;
@@ -312,6 +313,10 @@ struct GiCta
     iscr = reinterpret_cast<int *>(smem + p.off_iscr);
     stat = reinterpret_cast<signed char *>(smem + p.off_stat);
     eqf = reinterpret_cast<signed char *>(smem + p.off_eq);
+    Vp = smem + p.off_V;
+    bact = smem + p.off_bact;
+    hco = smem + p.off_hco;
+    alp = smem + p.off_alpha;
   }
 
   __device__ __forceinline__ void sync() const
@@ -508,6 +513,536 @@ struct GiCta
     q = 0;
     sync();
     return true;
+  }
+
+  // ==========================================================================================
+  // Warm-start capable initialisation: experimental::GoldfarbIdnaniSolver::init_
+  // (src/experimental/GoldfarbIdnaniSolver.cpp:66-111) and the functions it calls. The active
+  // normals N are reduced by B = L^-1 N, B = Q R (Householder, in place: R in the packed upper
+  // storage Rp, the essential parts of the Householder vectors in the packed strictly-lower storage
+  // Vp), J = L^-T Q; then the primal / dual point of the guessed active set. Arithmetic: the
+  // canonical order of oracle/warm_oracle.cpp, bit for bit.
+  // ==========================================================================================
+  __device__ __forceinline__ int offV(int k) const { return k * (n - 1) - ((k * (k - 1)) >> 1); } // column k of Vp: rows k+1 .. n-1
+
+  // element (i, k) of the n x q working matrix (B, then R over essential parts)
+  __device__ __forceinline__ double * Bat(int i, int k) const { return i <= k ? Rp + colR(k) + i : Vp + offV(k) + (i - k - 1); }
+
+  // processInitialActiveSet (src/experimental/GoldfarbIdnaniSolver.cpp:306-381). Returns the status.
+  __device__ int warm_active_set(long long b)
+  {
+    const bool use_as = P.as_in != nullptr && P.warm_start != 0;
+    const signed char * as = use_as ? P.as_in + b * P.s_as : nullptr;
+    const double big = P.big_bnd;
+    for(int c = tid; c < m; c += T)
+    {
+      int s = ST_INACTIVE;
+      if(c >= mc)
+      {
+        const int i = c - mc;
+        const double lo = xl[i], up = xu[i];
+        if(lo == up)
+          s = ST_FIXED;
+        else if(use_as)
+        {
+          const int g = as[c];
+          // FIXED is ignored (the bounds differ), so is a guess on an infinite bound; statuses that
+          // do not describe a bound are ignored too (the reference asserts on them)
+          if((g == ST_LOWER_BOUND && !(lo < -big)) || (g == ST_UPPER_BOUND && !(up > big))) s = g;
+        }
+      }
+      else
+      {
+        const double lo = bl[c], up = bu[c];
+        if(lo == up)
+          s = ST_EQUALITY;
+        else if(use_as)
+        {
+          const int g = as[c];
+          if((g == ST_LOWER && !(lo < -big)) || (g == ST_UPPER && !(up > big)) || g == ST_EQUALITY) s = g;
+        }
+      }
+      stat[c] = (signed char)s;
+    }
+    sync();
+    // ordered active list: bounds first, then general constraints (activation order of the reference)
+    if(warp == 0)
+    {
+      int cnt = 0, neq = 0;
+      for(int base = 0; base < m; base += 32)
+      {
+        const int o = base + lane; // position in activation order
+        const int c = o < nb ? mc + o : o - nb;
+        const int sv = o < m ? stat[c] : ST_INACTIVE;
+        const unsigned act = __ballot_sync(JRLQP_FULL, sv != ST_INACTIVE);
+        neq += __popc(__ballot_sync(JRLQP_FULL, sv == ST_EQUALITY || sv == ST_FIXED));
+        const int pos = cnt + __popc(act & ((1u << lane) - 1u));
+        // more than n guesses: positions >= n are kept in a spill that only the trimming below reads;
+        // alist has n entries, so the rare overflow case is resolved serially afterwards
+        if(sv != ST_INACTIVE && pos < n) alist[pos] = c;
+        cnt += __popc(act);
+      }
+      if(lane == 0)
+      {
+        iscr[0] = cnt;
+        iscr[1] = neq;
+      }
+    }
+    sync();
+    int cnt = iscr[0];
+    const int neq = iscr[1];
+    if(cnt > n)
+    {
+      if(neq > n) return TS_OVERCONSTRAINED_PROBLEM;
+      // "Work backward to deactivate inequality constraints until the number of constraints is nbVar":
+      // walking the activation order backwards, every non-equality entry is dropped until n remain.
+      if(tid == 0)
+      {
+        int excess = cnt - n;
+        for(int o = m - 1; o >= 0 && excess > 0; --o)
+        {
+          const int c = o < nb ? mc + o : o - nb;
+          const int sv = stat[c];
+          if(sv != ST_INACTIVE && sv != ST_EQUALITY && sv != ST_FIXED)
+          {
+            stat[c] = ST_INACTIVE;
+            --excess;
+          }
+        }
+        int pos = 0;
+        for(int o = 0; o < m; ++o)
+        {
+          const int c = o < nb ? mc + o : o - nb;
+          if(stat[c] != ST_INACTIVE) alist[pos++] = c;
+        }
+      }
+      cnt = n;
+      sync();
+    }
+    q = cnt;
+    return TS_SUCCESS;
+  }
+
+  // initializePrimalDualPoints (src/experimental/GoldfarbIdnaniSolver.cpp:461-486)
+  __device__ void warm_primal_dual(const double * ab)
+  {
+    const int j = tid, jc = min(tid, n - 1);
+    // alpha = J^T a, thread = column (cv holds a)
+    if(j < n) cv[j] = __ldg(ab + j);
+    sync();
+    {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const double * Jc = Jb + jc;
+      int i = 0;
+      for(; i + 3 < n; i += 4)
+      {
+        a0 = fma(Jc[i * ldj], cv[i], a0);
+        a1 = fma(Jc[(i + 1) * ldj], cv[i + 1], a1);
+        a2 = fma(Jc[(i + 2) * ldj], cv[i + 2], a2);
+        a3 = fma(Jc[(i + 3) * ldj], cv[i + 3], a3);
+      }
+      if(i < n) a0 = fma(Jc[i * ldj], cv[i], a0);
+      if(i + 1 < n) a1 = fma(Jc[(i + 1) * ldj], cv[i + 1], a1);
+      if(i + 2 < n) a2 = fma(Jc[(i + 2) * ldj], cv[i + 2], a2);
+      if(j < n) alp[j] = (a0 + a1) + (a2 + a3);
+    }
+    // beta = R^-T b_act on warp 0 (column-oriented forward substitution, true division), into zs
+    if(warp == 0)
+    {
+      double w[W];
+#pragma unroll
+      for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? bact[lane + 32 * s] : 0.0;
+      for(int k = 0; k < q; ++k)
+      {
+        const double bk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31) / Rp[colR(k) + k];
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          const int i = lane + 32 * s;
+          if(i == k)
+            w[s] = bk;
+          else if(i > k && i < q)
+            w[s] = fma(-bk, Rp[colR(i) + k], w[s]);
+        }
+      }
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+        if(lane + 32 * s < q) zs[lane + 32 * s] = w[s];
+    }
+    sync();
+    // x = J1 beta - J2 alpha2, thread = row ; d = alpha1 + beta (right-hand side of u)
+    {
+      const double * Jr = Jb + jc * ldj;
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      int c = 0;
+      for(; c + 3 < q; c += 4)
+      {
+        a0 = fma(Jr[c], zs[c], a0);
+        a1 = fma(Jr[c + 1], zs[c + 1], a1);
+        a2 = fma(Jr[c + 2], zs[c + 2], a2);
+        a3 = fma(Jr[c + 3], zs[c + 3], a3);
+      }
+      if(c < q) a0 = fma(Jr[c], zs[c], a0);
+      if(c + 1 < q) a1 = fma(Jr[c + 1], zs[c + 1], a1);
+      if(c + 2 < q) a2 = fma(Jr[c + 2], zs[c + 2], a2);
+      const double s1 = (a0 + a1) + (a2 + a3);
+      a0 = a1 = a2 = a3 = 0;
+      c = q;
+      for(; c + 3 < n; c += 4)
+      {
+        a0 = fma(Jr[c], alp[c], a0);
+        a1 = fma(Jr[c + 1], alp[c + 1], a1);
+        a2 = fma(Jr[c + 2], alp[c + 2], a2);
+        a3 = fma(Jr[c + 3], alp[c + 3], a3);
+      }
+      if(c < n) a0 = fma(Jr[c], alp[c], a0);
+      if(c + 1 < n) a1 = fma(Jr[c + 1], alp[c + 1], a1);
+      if(c + 2 < n) a2 = fma(Jr[c + 2], alp[c + 2], a2);
+      const double s2 = (a0 + a1) + (a2 + a3);
+      if(j < n) xs[j] = s1 - s2;
+      if(j < q) ds[j] = alp[j] + zs[j];
+    }
+    sync();
+    // u = R^-1 (alpha1 + beta)
+    if(warp == 0)
+    {
+      back_substitution();
+      __syncwarp();
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+        if(lane + 32 * s < q) us[lane + 32 * s] = rs[lane + 32 * s];
+    }
+    // f = beta.(0.5 beta + alpha1) - 0.5 |alpha2|^2 (dot32 order), every warp redundantly
+    {
+      double s1 = 0.0, s2 = 0.0;
+      for(int k = lane; k < q; k += 32)
+      {
+        const double bk = zs[k];
+        s1 = fma(bk, fma(0.5, bk, alp[k]), s1);
+      }
+      for(int k = lane; k < n - q; k += 32)
+      {
+        const double ak = alp[q + k];
+        s2 = fma(ak, ak, s2);
+      }
+      f = warp_sum32(s1) - 0.5 * warp_sum32(s2);
+    }
+    sync();
+  }
+
+  // experimental init_: returns the termination status (SUCCESS: ready for the main loop)
+  __device__ int init_warm(long long b, int & it)
+  {
+    const double * __restrict__ Gb = P.G + b * P.sG;
+    const double * __restrict__ ab = P.a + b * P.sa;
+    const int ldg = P.ldg;
+    const int i = tid;
+    const int ic = min(i, n - 1);
+
+    int st = warm_active_set(b);
+    if(st != TS_SUCCESS) return st;
+
+    // ---- Cholesky (same code path and order as init())
+#pragma unroll 4
+    for(int j = 0; j < n; ++j)
+      if(i < n && i >= j) Jb[i * ldj + j] = __ldg(Gb + i + (long long)j * ldg);
+    sync();
+    {
+      const double * Li = Jb + ic * ldj;
+#pragma unroll 1
+      for(int k = 0; k < n; ++k)
+      {
+        double v = 0.0;
+        if(32 * warp + 31 >= k)
+        {
+          const double * Lk = Jb + k * ldj;
+          double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+          int j = 0;
+#pragma unroll 1
+          for(; j + 3 < k; j += 4)
+          {
+            a0 = fma(Li[j], Lk[j], a0);
+            a1 = fma(Li[j + 1], Lk[j + 1], a1);
+            a2 = fma(Li[j + 2], Lk[j + 2], a2);
+            a3 = fma(Li[j + 3], Lk[j + 3], a3);
+          }
+          if(j < k) a0 = fma(Li[j], Lk[j], a0);
+          if(j + 1 < k) a1 = fma(Li[j + 1], Lk[j + 1], a1);
+          if(j + 2 < k) a2 = fma(Li[j + 2], Lk[j + 2], a2);
+          v = Li[k] - ((a0 + a1) + (a2 + a3));
+          if(i == k) scr[0] = v;
+        }
+        sync();
+        double vk = scr[0];
+        if(vk <= 0.0) return TS_NON_POS_HESSIAN;
+        double lkk = sqrt(vk);
+        if(i == k)
+        {
+          Jb[i * ldj + k] = lkk;
+          ldiag[k] = lkk;
+          rs[k] = 1.0 / lkk;
+        }
+        else if(i > k && i < n)
+          Jb[i * ldj + k] = v / lkk;
+        sync();
+      }
+    }
+    if(P.L != nullptr)
+    {
+      double * Lout = P.L + b * (long long)n * n;
+      for(int j = 0; j < n; ++j)
+        if(i < n && i >= j) Lout[i + (long long)j * n] = Jb[i * ldj + j];
+    }
+
+    // ---- J = L^-T in the upper triangle (diagonal of L kept in ldiag); L stays below for B = L^-1 N
+    {
+      const int j = i, jc = ic;
+      const int jmax = min(n - 1, 32 * warp + 31);
+      if(j < n) Jb[j * ldj + j] = rs[j];
+#pragma unroll 1
+      for(int r = jmax - 1; r >= 0; --r)
+      {
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 1
+        for(int k0 = r + 1; k0 <= jmax; k0 += 4)
+        {
+          const double * Jk = Jb + k0 * ldj;
+          const double t0 = fma(Jk[r], Jk[jc], a0);
+          const double t1 = fma(Jk[ldj + r], Jk[ldj + jc], a1);
+          const double t2 = fma(Jk[2 * ldj + r], Jk[2 * ldj + jc], a2);
+          const double t3 = fma(Jk[3 * ldj + r], Jk[3 * ldj + jc], a3);
+          a0 = k0 <= j ? t0 : a0;
+          a1 = k0 + 1 <= j ? t1 : a1;
+          a2 = k0 + 2 <= j ? t2 : a2;
+          a3 = k0 + 3 <= j ? t3 : a3;
+        }
+        if(r < j && j < n) Jb[r * ldj + j] = (-((a0 + a1) + (a2 + a3))) * rs[r];
+      }
+    }
+    sync();
+
+    // ---- active normals and b_act (initializeComputationData, :383-418), then B = L^-1 N,
+    //      thread = active column k
+    if(i < q)
+    {
+      const int k = i;
+      const int ci = alist[k];
+      const int sv = stat[ci];
+      double bk;
+      if(ci < mc)
+      {
+        const double * cg = P.C + b * P.sC + (long long)ci * P.ldc;
+        const bool neg = sv == ST_UPPER;
+        for(int r = 0; r < n; ++r)
+        {
+          const double v = cg[r];
+          *Bat(r, k) = neg ? -v : v;
+        }
+        bk = neg ? -bu[ci] : bl[ci];
+      }
+      else
+      {
+        const int pb = ci - mc;
+        const bool neg = sv == ST_UPPER_BOUND;
+        for(int r = 0; r < n; ++r) *Bat(r, k) = r == pb ? (neg ? -1.0 : 1.0) : 0.0;
+        bk = neg ? -xu[pb] : xl[pb];
+      }
+      bact[k] = bk;
+      // B(r,k) = (N(r,k) - dot4_{j<r}(L(r,j), B(j,k))) / L(r,r)
+      for(int r = 0; r < n; ++r)
+      {
+        const double * Lr = Jb + r * ldj;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        int j = 0;
+        for(; j + 3 < r; j += 4)
+        {
+          a0 = fma(Lr[j], *Bat(j, k), a0);
+          a1 = fma(Lr[j + 1], *Bat(j + 1, k), a1);
+          a2 = fma(Lr[j + 2], *Bat(j + 2, k), a2);
+          a3 = fma(Lr[j + 3], *Bat(j + 3, k), a3);
+        }
+        if(j < r) a0 = fma(Lr[j], *Bat(j, k), a0);
+        if(j + 1 < r) a1 = fma(Lr[j + 1], *Bat(j + 1, k), a1);
+        if(j + 2 < r) a2 = fma(Lr[j + 2], *Bat(j + 2, k), a2);
+        double * br = Bat(r, k);
+        *br = (*br - ((a0 + a1) + (a2 + a3))) / ldiag[r];
+      }
+    }
+    sync();
+    // L is no longer needed: clear the strict lower triangle of J
+    if(i < n)
+    {
+#pragma unroll 4
+      for(int c = 0; c < i; ++c) Jb[i * ldj + c] = 0.0;
+    }
+
+    // ---- Householder QR of B in place (unblocked), then rinv[k] = 1 / R(k,k)
+#pragma unroll 1
+    for(int k = 0; k < q; ++k)
+    {
+      const int len = n - k - 1;
+      double * ess = Vp + offV(k);
+      const double c0 = Rp[colR(k) + k];
+      double tsq = 0.0;
+      for(int t = lane; t < len; t += 32)
+      {
+        const double e = ess[t];
+        tsq = fma(e, e, tsq);
+      }
+      tsq = warp_sum32(tsq);
+      double tau, beta;
+      const bool degenerate = tsq <= 2.2250738585072014e-308;
+      if(degenerate)
+      {
+        tau = 0.0;
+        beta = c0;
+      }
+      else
+      {
+        beta = sqrt(fma(c0, c0, tsq));
+        if(c0 >= 0.0) beta = -beta;
+        tau = (beta - c0) / beta;
+      }
+      sync(); // everybody has read column k before it is rewritten
+      {
+        const double den = c0 - beta;
+        for(int t = tid; t < len; t += T) ess[t] = degenerate ? 0.0 : ess[t] / den;
+      }
+      if(tid == 0)
+      {
+        Rp[colR(k) + k] = beta;
+        hco[k] = tau;
+        rinv[k] = 1.0 / beta;
+      }
+      sync();
+      // apply H_k to the columns j > k, thread = column
+      for(int j = k + 1 + tid; j < q; j += T)
+      {
+        double * top = Rp + colR(j) + k;
+        if(len == 0)
+          *top = *top * (1.0 - tau);
+        else if(tau != 0.0)
+        {
+          double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+          int t = 0;
+          for(; t + 3 < len; t += 4)
+          {
+            a0 = fma(ess[t], *Bat(k + 1 + t, j), a0);
+            a1 = fma(ess[t + 1], *Bat(k + 2 + t, j), a1);
+            a2 = fma(ess[t + 2], *Bat(k + 3 + t, j), a2);
+            a3 = fma(ess[t + 3], *Bat(k + 4 + t, j), a3);
+          }
+          if(t < len) a0 = fma(ess[t], *Bat(k + 1 + t, j), a0);
+          if(t + 1 < len) a1 = fma(ess[t + 1], *Bat(k + 2 + t, j), a1);
+          if(t + 2 < len) a2 = fma(ess[t + 2], *Bat(k + 3 + t, j), a2);
+          const double tmp = ((a0 + a1) + (a2 + a3)) + *top;
+          *top = fma(-tau, tmp, *top);
+          for(int t2 = 0; t2 < len; ++t2)
+          {
+            double * e = Bat(k + 1 + t2, j);
+            *e = fma(-(tau * ess[t2]), tmp, *e);
+          }
+        }
+      }
+      sync();
+    }
+
+    // ---- J = J Q, thread = row (rows are independent: no barrier between reflectors)
+    if(i < n)
+    {
+      double * Jr = Jb + i * ldj;
+#pragma unroll 1
+      for(int k = 0; k < q; ++k)
+      {
+        const int len = n - k - 1;
+        const double * ess = Vp + offV(k);
+        const double tau = hco[k];
+        if(len == 0)
+          Jr[k] = Jr[k] * (1.0 - tau);
+        else if(tau != 0.0)
+        {
+          double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+          const double * Jt = Jr + k + 1;
+          int t = 0;
+          for(; t + 3 < len; t += 4)
+          {
+            a0 = fma(Jt[t], ess[t], a0);
+            a1 = fma(Jt[t + 1], ess[t + 1], a1);
+            a2 = fma(Jt[t + 2], ess[t + 2], a2);
+            a3 = fma(Jt[t + 3], ess[t + 3], a3);
+          }
+          if(t < len) a0 = fma(Jt[t], ess[t], a0);
+          if(t + 1 < len) a1 = fma(Jt[t + 1], ess[t + 1], a1);
+          if(t + 2 < len) a2 = fma(Jt[t + 2], ess[t + 2], a2);
+          const double tmp = ((a0 + a1) + (a2 + a3)) + Jr[k];
+          Jr[k] = fma(-tau, tmp, Jr[k]);
+          const double tt = tau * tmp;
+          for(int t2 = 0; t2 < len; ++t2) Jr[k + 1 + t2] = fma(-tt, ess[t2], Jr[k + 1 + t2]);
+        }
+      }
+    }
+    sync();
+
+    warm_primal_dual(ab);
+
+    // ---- constraints activated with a negative multiplier are dropped, most negative first (:83-108)
+#pragma unroll 1
+    for(;;)
+    {
+      double bu_ = -1e-14;
+      int bl_ = JRLQP_NONE;
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        const int l = lane + 32 * s;
+        if(l < q)
+        {
+          const int sv = stat[alist[l]];
+          const double ul = us[l];
+          if(ul < bu_ && sv != ST_FIXED && sv != ST_EQUALITY)
+          {
+            bu_ = ul;
+            bl_ = l;
+          }
+        }
+      }
+#pragma unroll
+      for(int off = 16; off >= 1; off >>= 1)
+      {
+        const double ou = __shfl_xor_sync(JRLQP_FULL, bu_, off);
+        const int ol = __shfl_xor_sync(JRLQP_FULL, bl_, off);
+        if(ou < bu_ || (ou == bu_ && ol < bl_))
+        {
+          bu_ = ou;
+          bl_ = ol;
+        }
+      }
+      const int lmin = __shfl_sync(JRLQP_FULL, bl_, 0);
+      if(lmin == JRLQP_NONE) break;
+      ++it;
+      sync();
+      // b_act.segment(lmin, q-1-lmin) = b_act.tail(q-1-lmin)
+      if(warp == 0)
+      {
+        double bt[W];
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          const int k = lane + 32 * s;
+          bt[s] = (k >= lmin && k + 1 < q) ? bact[k + 1] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for(int s = 0; s < W; ++s)
+        {
+          const int k = lane + 32 * s;
+          if(k >= lmin && k + 1 < q) bact[k] = bt[s];
+        }
+      }
+      remove_constraint(lmin);
+      warm_primal_dual(ab);
+    }
+    return TS_SUCCESS;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1218,17 +1753,31 @@ struct GiCta
     cvec = ((reinterpret_cast<unsigned long long>(Cb) & 15ull) == 0ull) && ((ldC & 1) == 0);
 
     PH_DECL;
-    const bool init_ok = init(b);
-    PH_MARK(0);
-    if(!init_ok)
-    {
-      write_failure(b, TS_NON_POS_HESSIAN);
-      return;
-    }
-
-    int status = TS_MAX_ITER_REACHED;
     int it = 0;
     int cursor = 0; // next constraint / bound to test for pre-activation; m when that phase is over
+    if(WARM)
+    {
+      // experimental::GoldfarbIdnaniSolver: the equalities are part of the initial factorisation
+      const int st0 = init_warm(b, it);
+      if(st0 != TS_SUCCESS)
+      {
+        write_failure(b, st0);
+        return;
+      }
+      cursor = m;
+    }
+    else
+    {
+      const bool init_ok = init(b);
+      if(!init_ok)
+      {
+        write_failure(b, TS_NON_POS_HESSIAN);
+        return;
+      }
+    }
+    PH_MARK(0);
+
+    int status = TS_MAX_ITER_REACHED;
     bool skip = false;
     bool have_sel = false; // the constraint of this iteration was already selected at the end of the previous one
     Sel sc{-1, ST_INACTIVE};
@@ -1445,11 +1994,11 @@ struct GiCta
 
 // Persistent kernel: grid = resident CTAs of the whole GPU; every CTA pulls the next problem index
 // from an atomic ticket counter, which absorbs the divergent iteration counts across QPs.
-template<int W, bool STAGE_C>
-__global__ void __launch_bounds__(32 * W, (W == 1 ? 16 : (W == 2 ? 6 : 1))) gi_dense_cta_kernel(const GiParams p)
+template<int W, bool STAGE_C, bool WARM = false>
+__global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? 16 : (W == 2 ? 6 : 1)))) gi_dense_cta_kernel(const GiParams p)
 {
   extern __shared__ __align__(16) double smem[];
-  GiCta<W, STAGE_C> cta(p, smem);
+  GiCta<W, STAGE_C, WARM> cta(p, smem);
   unsigned long long * ticket = reinterpret_cast<unsigned long long *>(smem + p.off_scr + 12);
   for(;;)
   {

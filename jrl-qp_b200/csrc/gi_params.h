@@ -52,6 +52,9 @@ struct GiParams
   long long sxl;
   const double * xu;
   long long sxu;
+  const signed char * as_in; // warm start: initial activation status guess (nullable), int8 x (mc + nb)
+  long long s_as;
+  int warm_start; // SolverOptions::warmStart_
   // outputs (device pointers, dense; nullable except x)
   double * x;
   double * u;
@@ -70,7 +73,8 @@ struct GiParams
   int ldcs; // leading dimension of the staged C (odd), if staged
   int npad; // threads per CTA (>= n)
   int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_rinv, off_scr, off_C; // offsets in doubles
-  int off_alist, off_gk, off_iscr, off_stat, off_eq; // offsets in doubles of the int / int8 arrays
+  int off_alist, off_gk, off_iscr, off_stat, off_eq;
+  int off_V, off_bact, off_hco, off_alpha; // warm-start kernels only (offsets in doubles) // offsets in doubles of the int / int8 arrays
 };
 
 } // namespace jrlqp

@@ -109,6 +109,7 @@ EXPORTED_SYMBOLS = [
     "jrlqp_structured_create", "jrlqp_structured_destroy", "jrlqp_structured_last_error",
     "jrlqp_structured_llt_device", "jrlqp_structured_llt_host", "jrlqp_structured_solve_device",
     "jrlqp_structured_solve_host", "jrlqp_structured_get_info", "jrlqp_selftest_arith",
+    "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host",
 ]
 
 _lib = None
@@ -137,6 +138,8 @@ def load_library():
         lib.jrlqp_set_stage_c.argtypes = [C.c_void_p, C.c_int32]
         lib.jrlqp_solve_batch_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
         lib.jrlqp_solve_batch_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
+        lib.jrlqp_solve_batch_warm_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
+        lib.jrlqp_solve_batch_warm_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
         lib.jrlqp_structured_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int32]
         lib.jrlqp_structured_destroy.argtypes = [C.c_void_p]
         lib.jrlqp_structured_last_error.restype = C.c_char_p
@@ -250,8 +253,11 @@ class BatchedGoldfarbIdnaniSolver:
         pb.as_in, pb.as_stride = None, 0
         return pb
 
-    def solve(self, G, a, Cm, bl, bu, xl=None, xu=None, want_L=False, want_active_list=True):
-        """HOST arrays (numpy). Returns the worst TerminationStatus; results in self.last (dict)."""
+    def solve(self, G, a, Cm, bl, bu, xl=None, xu=None, want_L=False, want_active_list=True, experimental=False, as_in=None):
+        """HOST arrays (numpy). Returns the worst TerminationStatus; results in self.last (dict).
+        experimental=True runs the warm-start capable solver (experimental::GoldfarbIdnaniSolver::solve):
+        as_in [B, mc+nb] int8 (or [mc+nb], shared) is the guessed active set, honoured when
+        options().warmStart() is set."""
         f64 = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
         G, a, Cm, bl, bu, xl, xu = map(f64, (G, a, Cm, bl, bu, xl, xu))
         if self.nb == 0:
@@ -275,7 +281,16 @@ class BatchedGoldfarbIdnaniSolver:
         L = np.zeros((B, n, n)) if want_L else None
         pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, shared)
         res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(it), _ptr(status), _ptr(act), _ptr(alist), _ptr(nact), _ptr(L))
-        rc = self._lib.jrlqp_solve_batch_host(self._h, C.byref(pb), C.byref(res))
+        if experimental:
+            if as_in is not None:
+                as_in = np.ascontiguousarray(as_in, dtype=np.int8)
+                if as_in.shape[-1] != m:
+                    raise JrlQpError("as_in must have nbCstr + nbBnd entries per instance")
+                pb.as_in, pb.as_stride = _ptr(as_in), (m if as_in.ndim == 2 else 0)
+            fn = self._lib.jrlqp_solve_batch_warm_host
+        else:
+            fn = self._lib.jrlqp_solve_batch_host
+        rc = fn(self._h, C.byref(pb), C.byref(res))
         if rc < 0:
             raise JrlQpError(f"jrlqp_solve_batch_host failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
         self.last = dict(x=x, u=u, f=f, iterations=it, status=status, active_set=act, active_list=alist,
@@ -328,7 +343,9 @@ class GoldfarbIdnaniSolver:
             self._impl.options(opt)
         return self
 
-    def solve(self, G, a, Cmat, bl, bu, xl, xu):
+    _experimental = False
+
+    def solve(self, G, a, Cmat, bl, bu, xl, xu, as_=None):
         G = np.asarray(G)
         n = G.shape[0]
         Cmat = np.asarray(Cmat, dtype=np.float64).reshape(n, -1)
@@ -342,13 +359,19 @@ class GoldfarbIdnaniSolver:
                               np.asarray(bl, dtype=np.float64)[None] if nbCstr else None,
                               np.asarray(bu, dtype=np.float64)[None] if nbCstr else None,
                               np.asarray(xl, dtype=np.float64)[None] if useBnd else None,
-                              np.asarray(xu, dtype=np.float64)[None] if useBnd else None, want_L=True)
+                              np.asarray(xu, dtype=np.float64)[None] if useBnd else None, want_L=True,
+                              **self._extra(as_, nbCstr + (n if useBnd else 0)))
         self._res = self._impl.last
         if st != TerminationStatus.NON_POS_HESSIAN and isinstance(G, np.ndarray) and G.dtype == np.float64 and G.flags.writeable:
             Lf = self._res["L"][0].T  # back to (i, j) indexing
             il = np.tril_indices(n)
             G[il] = Lf[il]  # G is an in/out argument in the reference (src/GoldfarbIdnaniSolver.cpp:58)
         return st
+
+    def _extra(self, as_, m):
+        if as_ is not None and len(as_) > 0:
+            raise JrlQpError("the stable GoldfarbIdnaniSolver takes no active-set guess; use experimental.GoldfarbIdnaniSolver")
+        return {}
 
     def solution(self):
         return self._res["x"][0]
@@ -367,3 +390,27 @@ class GoldfarbIdnaniSolver:
 
     def resetActiveSet(self):
         pass  # the stable solver resets its active set at every solve (src/GoldfarbIdnaniSolver.cpp:75)
+
+
+class ExperimentalGoldfarbIdnaniSolver(GoldfarbIdnaniSolver):
+    """Mirror of jrl::qp::experimental::GoldfarbIdnaniSolver (include/jrl-qp/experimental/GoldfarbIdnaniSolver.h:15-39):
+    solve(G, a, C, bl, bu, xl, xu, as=[]) with SolverOptions::warmStart. With warm start on and an empty
+    `as`, the active set of the previous solve is reused (src/experimental/GoldfarbIdnaniSolver.cpp:58-61)."""
+
+    def _extra(self, as_, m):
+        if as_ is not None and len(as_) > 0:
+            if not self._opt.warmStart_:
+                raise JrlQpError("Non-empty active set used with cold start option.")  # the reference asserts
+            guess = np.array([int(v) for v in as_], dtype=np.int8)
+        elif self._opt.warmStart_ and self._res is not None and self._res["active_set"].shape[1] == m:
+            guess = self._res["active_set"][0].copy()
+        else:
+            guess = None
+        return {"experimental": True, "as_in": None if guess is None else guess[None]}
+
+    def resetActiveSet(self):
+        self._res = None  # DualSolver::resetActiveSet (src/DualSolver.cpp:85-88)
+
+
+class experimental:  # namespace jrl::qp::experimental
+    GoldfarbIdnaniSolver = ExperimentalGoldfarbIdnaniSolver

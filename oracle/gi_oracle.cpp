@@ -236,7 +236,12 @@ TerminationStatus GIOracle::solve(double * G,
   needExpand_ = true;
   it_ = 0;
   if(!init()) return NON_POS_HESSIAN;
+  return mainLoop();
+}
 
+// src/DualSolver.cpp:96-168 — the loop shared by the cold solver and the experimental (warm) one.
+TerminationStatus GIOracle::mainLoop()
+{
   const int n = n_;
   bool skipStep1 = false;
   Selected sc;
@@ -671,13 +676,18 @@ void GIOracle::addConstraint(Selected sc)
 void GIOracle::removeConstraint(int l)
 {
   // src/DualSolver.cpp:237-244
-  const int n = n_;
   int q = A_.nbActiveCstr();
   double * u = u_.data();
   for(int k = l; k < q; ++k) u[k] = u[k + 1];
   A_.deactivate(l);
-  // src/GoldfarbIdnaniSolver.cpp:239-256
-  q = A_.nbActiveCstr(); // after removal
+  removeConstraintCore(l);
+}
+
+void GIOracle::removeConstraintCore(int l)
+{
+  // src/GoldfarbIdnaniSolver.cpp:239-256 (removeConstraint_)
+  const int n = n_;
+  int q = A_.nbActiveCstr(); // after removal
   double * J = J_.data();
   double * R = R_.data();
   for(int i = l; i < q; ++i)

@@ -163,6 +163,21 @@ public:
                           const double * xl,
                           const double * xu);
 
+  /** experimental::GoldfarbIdnaniSolver::solve (src/experimental/GoldfarbIdnaniSolver.cpp:21-64), the
+   * warm-start capable variant: `as` (nullable, nbCstr + nbBnd entries, general constraints first) is the
+   * initial guess of the active set; with options().warmStart and as == nullptr the previous active set
+   * of this object is reused. See warm_oracle.cpp for the restated functions and arithmetic. */
+  TerminationStatus solveExperimental(double * G,
+                                      int ldg,
+                                      const double * a,
+                                      const double * C,
+                                      int ldc,
+                                      const double * bl,
+                                      const double * bu,
+                                      const double * xl,
+                                      const double * xu,
+                                      const int8_t * as);
+
   const double * solution() const { return x_.data(); }
   const double * multipliers(); // expanded, signed (src/DualSolver.cpp:38-69)
   double objectiveValue() const { return f_; }
@@ -196,6 +211,13 @@ private:
   double normalDot(Selected sc, const double * v) const; // ConstraintNormal::dot
   void addConstraint(Selected sc);
   void removeConstraint(int l);
+  void removeConstraintCore(int l);
+  TerminationStatus mainLoop();
+  // experimental solver (warm_oracle.cpp)
+  TerminationStatus initExperimental();
+  TerminationStatus processInitialActiveSet();
+  void initializeComputationData();
+  void initializePrimalDualPoints();
   void noteMargin(double a, double b);
 
   SolverOptions opt_;
@@ -207,6 +229,8 @@ private:
   const double *a_ = nullptr, *C_ = nullptr, *bl_ = nullptr, *bu_ = nullptr, *xl_ = nullptr, *xu_ = nullptr;
   // workspaces
   std::vector<double> x_, z_, d_, w_, u_, r_, J_, R_, uExp_, acc_;
+  std::vector<double> bact_, hcoef_, alpha_; // experimental solver
+  std::vector<ActivationStatus> asIn_; // pb_.as
   double f_ = 0;
   int it_ = 0;
   bool needExpand_ = false;

@@ -22,8 +22,12 @@ extern "C"
  * nb is 0 (no bounds) or n. Outputs are dense: x[batch][n], u[batch][mc+nb], ...
  * Returns the worst status.
  */
-int gi_oracle_solve_batch(int n,
-                          int mc,
+static int solve_batch_impl(const signed char * as,
+                            long sas,
+                            int experimental,
+                            int warm_start,
+                            int n,
+                            int mc,
                           int nb,
                           long batch,
                           const double * G,
@@ -70,6 +74,7 @@ int gi_oracle_solve_batch(int n,
     SolverOptions opt;
     opt.maxIter = max_iter;
     opt.bigBnd = big_bnd;
+    opt.warmStart = warm_start != 0;
     solver.options(opt);
     solver.instrument(instr);
     std::vector<double> Gs(static_cast<size_t>(n) * n);
@@ -84,10 +89,20 @@ int gi_oracle_solve_batch(int n,
       {
         const double * Gb = G + b * sG;
         for(int j = 0; j < n; ++j) std::memcpy(Gs.data() + static_cast<size_t>(j) * n, Gb + static_cast<size_t>(j) * ldg, sizeof(double) * n);
-        int st = solver.solve(Gs.data(), n, a + b * sa, C + b * sC, ldc, bl + b * sbl, bu + b * sbu, nb ? xl + b * sxl : nullptr,
-                              nb ? xu + b * sxu : nullptr);
+        int st;
+        if(experimental)
+        {
+          // one solver object per thread is re-used across instances: "reuse the previous active set"
+          // (as == nullptr with warm start) is therefore not meaningful here and is replaced by an empty guess
+          solver.resetActiveSet();
+          st = solver.solveExperimental(Gs.data(), n, a + b * sa, C + b * sC, ldc, bl + b * sbl, bu + b * sbu, nb ? xl + b * sxl : nullptr,
+                                        nb ? xu + b * sxu : nullptr, as ? reinterpret_cast<const int8_t *>(as + b * sas) : nullptr);
+        }
+        else
+          st = solver.solve(Gs.data(), n, a + b * sa, C + b * sC, ldc, bl + b * sbl, bu + b * sbu, nb ? xl + b * sxl : nullptr,
+                            nb ? xu + b * sxu : nullptr);
         localWorst = std::max(localWorst, st);
-        if(st == NON_POS_HESSIAN)
+        if(st == NON_POS_HESSIAN || st == OVERCONSTRAINED_PROBLEM)
         {
           // The reference leaves x/u/f/active set unspecified (stale) when the factorisation fails
           // (src/DualSolver.cpp:93-94); both the oracle and the CUDA path report zeros / empty set.
@@ -139,6 +154,28 @@ int gi_oracle_solve_batch(int n,
     for(auto & t : th) t.join();
   }
   return worst.load();
+}
+
+#define GI_BATCH_PARAMS                                                                                                          \
+  int n, int mc, int nb, long batch, const double *G, long sG, int ldg, const double *a, long sa, const double *C, long sC,     \
+      int ldc, const double *bl, long sbl, const double *bu, long sbu, const double *xl, long sxl, const double *xu, long sxu,  \
+      int max_iter, double big_bnd, double *x, double *u, double *f, int *iters, int *status, signed char *act,                 \
+      int *active_list, int *nactive, double *L_out, double *flops, double *margin, int nthreads
+#define GI_BATCH_ARGS                                                                                                        \
+  n, mc, nb, batch, G, sG, ldg, a, sa, C, sC, ldc, bl, sbl, bu, sbu, xl, sxl, xu, sxu, max_iter, big_bnd, x, u, f, iters,   \
+      status, act, active_list, nactive, L_out, flops, margin, nthreads
+
+/** GoldfarbIdnaniSolver::solve over a batch (see solve_batch_impl). */
+int gi_oracle_solve_batch(GI_BATCH_PARAMS)
+{
+  return solve_batch_impl(nullptr, 0, 0, 0, GI_BATCH_ARGS);
+}
+
+/** experimental::GoldfarbIdnaniSolver::solve over a batch: `as` (nullable) = initial active-set guess,
+ * int8 x (mc + nb) per instance, `sas` elements apart; warm_start = SolverOptions::warmStart_. */
+int gi_oracle_solve_batch_warm(const signed char * as, long sas, int warm_start, GI_BATCH_PARAMS)
+{
+  return solve_batch_impl(as, sas, 1, warm_start, GI_BATCH_ARGS);
 }
 
 /** Single solve with the per-iteration event trace (debugging aid for parity work).

@@ -51,11 +51,13 @@ def _stride(a, per):
 
 
 def solve_batch(G, a, Cm, bl, bu, xl=None, xu=None, max_iter=500, big_bnd=1e100, nthreads=1,
-                want_L=False, instrument=False):
+                want_L=False, instrument=False, experimental=False, warm_start=False, as_in=None):
     """G: [B,n,n] (each n x n block column-major, i.e. G[b, j, i] = G_b(i, j); symmetric input makes
     this immaterial), a: [B,n], Cm: [B,mc,n] (row i = constraint normal i = column i of the reference's
     n x mc column-major C), bl/bu: [B,mc], xl/xu: [B,n] or None. Arrays with one dimension less are
     shared by all instances (stride 0). Returns a dict of numpy arrays.
+    experimental=True runs the restatement of experimental::GoldfarbIdnaniSolver (warm-start capable):
+    as_in [B, mc+nb] int8 is the initial active-set guess (used only with warm_start=True).
     """
     G = _f64(G)
     a = _f64(a)
@@ -87,8 +89,17 @@ def solve_batch(G, a, Cm, bl, bu, xl=None, xu=None, max_iter=500, big_bnd=1e100,
         Cm = np.zeros((1,))
         bl = np.zeros((1,))
         bu = np.zeros((1,))
-    worst = lib().gi_oracle_solve_batch(
-        C.c_int(n), C.c_int(mc), C.c_int(nb), C.c_long(B),
+    fn = lib().gi_oracle_solve_batch
+    pre = []
+    if experimental:
+        fn = lib().gi_oracle_solve_batch_warm
+        if as_in is not None:
+            as_in = np.ascontiguousarray(as_in, dtype=np.int8)
+            assert as_in.shape[-1] == m
+        pre = [None if as_in is None else as_in.ctypes.data_as(c_bp), C.c_long(m if (as_in is not None and as_in.ndim == 2) else 0),
+               C.c_int(1 if warm_start else 0)]
+    worst = fn(
+        *pre, C.c_int(n), C.c_int(mc), C.c_int(nb), C.c_long(B),
         _dp(G), C.c_long(_stride(G, n * n) if G.ndim == 3 else 0), C.c_int(n),
         _dp(a), C.c_long(n if a.ndim == 2 else 0),
         _dp(Cm), C.c_long(mc * n if Cm.ndim == 3 else 0), C.c_int(n),
