@@ -138,7 +138,9 @@ typedef struct jrlqp_solver jrlqp_solver;
 /* GoldfarbIdnaniSolver(nbVar, nbCstr, useBounds) (include/jrl-qp/GoldfarbIdnaniSolver.h:17-19)
  * + DualSolver::resize. batch_capacity bounds the batch of the *_host entry points (device staging
  * buffers are allocated once here, honouring the reference's no-allocation-in-solve contract,
- * tests/GoldfarbIdnaniSolverTest.cpp:113-117). device = CUDA ordinal. n <= 128. */
+ * tests/GoldfarbIdnaniSolverTest.cpp:113-117). device = CUDA ordinal. n <= 1024: problems with
+ * n <= 128 keep J and R in shared memory for the whole solve; larger ones (the reference's MultiIK
+ * fixtures, n = 387 / 210) use a per-CTA workspace in global memory (L2-resident). */
 int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds, int64_t batch_capacity, int32_t device);
 int jrlqp_destroy(jrlqp_solver * s);
 
@@ -169,7 +171,8 @@ int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrl
  * reference (FIXED on distinct bounds, a side whose bound is infinite); statuses of the wrong kind
  * (a bound status on a general constraint or vice versa), on which the reference asserts, are ignored.
  * JRLQP_OVERCONSTRAINED_PROBLEM is reported per instance when more than n equalities are given.
- * Needs n (n - 1) / 2 more doubles of shared memory than the cold kernel (n <= ~100). */
+ * The shared-memory kernel needs n (n - 1) / 2 more doubles of shared memory than the cold one
+ * (n <= ~100); beyond that, select the global-workspace kernel (automatic for n > 128). */
 int jrlqp_solve_batch_warm_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream);
 int jrlqp_solve_batch_warm_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res);
 
@@ -188,6 +191,10 @@ typedef struct jrlqp_kernel_info
 int jrlqp_get_kernel_info(const jrlqp_solver * s, jrlqp_kernel_info * info);
 /* Tuning knob: 0 = C read from global/L2, 1 = staged in shared memory, -1 = automatic. */
 int jrlqp_set_stage_c(jrlqp_solver * s, int32_t mode);
+/* Kernel family: 0 = automatic (n <= 128: shared-memory kernel, else global-workspace kernel),
+ * 1 = shared-memory kernel (n <= 128), 2 = global-workspace kernel (any n <= 1024; used by the tests
+ * to cross-check the two families on the same problems — their results are bit-identical). */
+int jrlqp_set_kernel_path(jrlqp_solver * s, int32_t mode);
 /* Number of kernels this library has launched since it was loaded (all solvers). */
 int64_t jrlqp_launch_count(void);
 /* Last CUDA error string seen by this solver ("" if none). */

@@ -2,6 +2,7 @@
 // dispatch, and the host-pointer entry point that pipelines H2D copies, the persistent kernel and
 // D2H copies over a few streams. Pure CUDA runtime — no PyTorch, no CPU fallback.
 #include "gi_dense_cta.cuh"
+#include "gi_large.cuh"
 #include "jrlqp_b200.h"
 
 #include <algorithm>
@@ -158,6 +159,16 @@ struct jrlqp_solver
   int wsmem_bytes = 0;
   int wocc = 0;
   signed char * d_as = nullptr; // staging of as_in for the host entry point
+  // large-n kernel (gi_large.cuh): J, L and R live in a per-CTA global-memory workspace
+  int path_mode = 0; // 0 automatic (n <= 128: shared-memory kernel), 1 shared-memory kernel, 2 global-workspace kernel
+  bool large = false;
+  int lsmem_bytes[2] = {0, 0}, locc[2] = {0, 0}, lregs[2] = {0, 0}; // [cold, warm]
+  double * d_work[2] = {nullptr, nullptr};
+  int * d_busy[2] = {nullptr, nullptr};
+  int work_slots[2] = {0, 0};
+  long long work_stride[2] = {0, 0};
+  // capacity (instances) of every staging buffer of the host entry point: 1 for arrays shared by the batch
+  long long cap_G = 0, cap_a = 0, cap_C = 0, cap_bl = 0, cap_bu = 0, cap_xl = 0, cap_xu = 0, cap_out = 0, cap_L = 0;
   int num_sms = 0;
   int regs = 0;
   int max_smem_optin = 0;
@@ -172,6 +183,7 @@ struct jrlqp_solver
   signed char * d_act = nullptr;
   bool staging_ready = false;
   cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_shared = nullptr;
   std::string err;
 
   bool check(cudaError_t e, const char * what)
@@ -188,8 +200,62 @@ struct jrlqp_solver
     if(!s->check((call), #call)) return JRLQP_ERR_CUDA; \
   } while(0)
 
+static constexpr int kLargeThreads = 256;
+
+// Large-n kernel: shared-memory size, residency and the per-CTA global workspace (allocated on first use)
+static int configure_large(jrlqp_solver * s, bool warm)
+{
+  const int w = warm ? 1 : 0;
+  if(s->d_work[w]) return JRLQP_OK;
+  KernelFn fn = warm ? gi_large_kernel<kLargeThreads, true> : gi_large_kernel<kLargeThreads, false>;
+  const LargeSmem lay(s->n, s->m, warm);
+  const int smem = lay.total * 8;
+  if(smem > s->max_smem_optin)
+  {
+    s->err = "large-n kernel: the vectors do not fit in shared memory";
+    return JRLQP_ERR_ARG;
+  }
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kLargeThreads, smem));
+  if(occ < 1)
+  {
+    s->err = "large-n kernel cannot be made resident";
+    return JRLQP_ERR_ARG;
+  }
+  const int slots = occ * s->num_sms; // every resident CTA of this kernel, whatever the launch, finds a slice
+  occ = std::min(occ, 2);
+  cudaFuncAttributes attr;
+  CK(cudaFuncGetAttributes(&attr, fn));
+  s->lregs[w] = attr.numRegs;
+  s->lsmem_bytes[w] = smem;
+  s->locc[w] = occ;
+  s->work_stride[w] = large_workspace_doubles(s->n, warm);
+  s->work_slots[w] = slots;
+  CK(cudaMalloc(&s->d_busy[w], sizeof(int) * (size_t)slots));
+  CK(cudaMemset(s->d_busy[w], 0, sizeof(int) * (size_t)slots));
+  CK(cudaMalloc(&s->d_work[w], sizeof(double) * (size_t)s->work_stride[w] * (size_t)slots));
+  return JRLQP_OK;
+}
+
 static int configure_kernel(jrlqp_solver * s)
 {
+  if(s->n > 128 && s->path_mode == 1)
+  {
+    s->err = "the shared-memory kernel needs n <= 128";
+    return JRLQP_ERR_ARG;
+  }
+  s->large = s->path_mode == 2 || (s->path_mode == 0 && s->n > 128);
+  if(s->large)
+  {
+    int rc = configure_large(s, false);
+    if(rc != JRLQP_OK) return rc;
+    s->occ = s->locc[0];
+    s->smem_bytes = s->lsmem_bytes[0];
+    s->regs = s->lregs[0];
+    s->stage = false;
+    return JRLQP_OK;
+  }
   // choose staging of C: automatic mode stages it when that costs no residency
   auto try_cfg = [&](bool stage, int & occ, int & smem, KernelFn & fn, Layout & lay) -> int
   {
@@ -268,7 +334,7 @@ int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds,
 {
   if(!out) return JRLQP_ERR_ARG;
   *out = nullptr;
-  if(n < 1 || n > 128 || mc < 0 || batch_capacity < 0) return JRLQP_ERR_ARG;
+  if(n < 1 || n > 1024 || mc < 0 || batch_capacity < 0) return JRLQP_ERR_ARG;
   jrlqp_solver * s = new jrlqp_solver();
   s->n = n;
   s->mc = mc;
@@ -276,7 +342,7 @@ int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds,
   s->m = mc + s->nb;
   s->capacity = batch_capacity;
   s->device = device;
-  s->warps = (n + 31) / 32;
+  s->warps = std::min((n + 31) / 32, 4);
   jrlqp_default_options(&s->opt);
   *out = s; // returned even on CUDA failure so that jrlqp_last_error is readable
   int ndev = 0;
@@ -312,12 +378,13 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
   for(int i = 0; i < kStreams; ++i)
     if(s->streams[i]) cudaStreamDestroy(s->streams[i]);
+  if(s->ev_shared) cudaEventDestroy(s->ev_shared);
   delete s;
   return JRLQP_OK;
 }
@@ -344,11 +411,20 @@ int jrlqp_set_stage_c(jrlqp_solver * s, int32_t mode)
   return configure_kernel(s);
 }
 
+int jrlqp_set_kernel_path(jrlqp_solver * s, int32_t mode)
+{
+  if(!s || mode < 0 || mode > 2) return JRLQP_ERR_ARG;
+  s->path_mode = mode;
+  s->wkernel = nullptr;
+  cudaSetDevice(s->device);
+  return configure_kernel(s);
+}
+
 int jrlqp_get_kernel_info(const jrlqp_solver * s, jrlqp_kernel_info * info)
 {
   if(!s || !info) return JRLQP_ERR_ARG;
-  info->threads_per_qp = 32 * s->warps;
-  info->rows_per_thread = 1;
+  info->threads_per_qp = s->large ? kLargeThreads : 32 * s->warps;
+  info->rows_per_thread = s->large ? (s->n + kLargeThreads - 1) / kLargeThreads : 1;
   info->smem_bytes_per_qp = s->smem_bytes;
   info->qps_per_sm = s->occ;
   info->grid = s->occ * s->num_sms;
@@ -396,7 +472,12 @@ static int configure_warm(jrlqp_solver * s);
 
 static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter, bool warm = false)
 {
-  if(warm)
+  if(s->large)
+  {
+    int rc = configure_large(s, warm);
+    if(rc != JRLQP_OK) return rc;
+  }
+  else if(warm)
   {
     int rc = configure_warm(s);
     if(rc != JRLQP_OK) return rc;
@@ -465,10 +546,21 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.off_bact = lay.off_bact;
   p.off_hco = lay.off_hco;
   p.off_alpha = lay.off_alpha;
-  const int occ = warm ? s->wocc : s->occ;
+  const int occ = s->large ? s->locc[warm ? 1 : 0] : (warm ? s->wocc : s->occ);
   long long grid = std::min<long long>((long long)occ * s->num_sms, std::max<long long>(pb->batch, 1));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-  if(warm)
+  if(s->large)
+  {
+    p.work = s->d_work[warm ? 1 : 0];
+    p.work_stride = s->work_stride[warm ? 1 : 0];
+    p.work_busy = s->d_busy[warm ? 1 : 0];
+    p.work_slots = s->work_slots[warm ? 1 : 0];
+    if(warm)
+      gi_large_kernel<kLargeThreads, true><<<(unsigned)grid, kLargeThreads, s->lsmem_bytes[1], st>>>(p);
+    else
+      gi_large_kernel<kLargeThreads, false><<<(unsigned)grid, kLargeThreads, s->lsmem_bytes[0], st>>>(p);
+  }
+  else if(warm)
     s->wkernel<<<(unsigned)grid, 32 * s->warps, s->wsmem_bytes, st>>>(p);
   else
     s->kernel<<<(unsigned)grid, 32 * s->warps, s->smem_bytes, st>>>(p);
@@ -523,25 +615,40 @@ int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const j
   return launch(s, pb, res, (cudaStream_t)stream, counter);
 }
 
-static int ensure_staging(jrlqp_solver * s, bool wantL)
+// Device staging of the host entry point. Inputs shared by the whole batch (stride 0) take ONE slot, so a
+// shared 387 x 387 Hessian with a 256k batch capacity costs 1.2 MB, not 300 GB; the buffers only grow.
+static int ensure_buffer(jrlqp_solver * s, double ** buf, long long * cap, long long count, long long per)
+{
+  if(count <= *cap) return JRLQP_OK;
+  if(*buf) CK(cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  CK(cudaMalloc(buf, sizeof(double) * (size_t)std::max<long long>(count * per, 1)));
+  *cap = count;
+  return JRLQP_OK;
+}
+
+static int ensure_staging(jrlqp_solver * s, const jrlqp_problem * pb, bool wantL)
 {
   const long long B = std::max<long long>(s->capacity, 1);
   const long long n = s->n, mc = s->mc, m = s->m;
+  auto cnt = [&](long long stride) { return stride == 0 ? 1ll : B; };
+  int rc;
+  if((rc = ensure_buffer(s, &s->d_G, &s->cap_G, cnt(pb->G_stride), n * n)) != JRLQP_OK) return rc;
+  if((rc = ensure_buffer(s, &s->d_a, &s->cap_a, cnt(pb->a_stride), n)) != JRLQP_OK) return rc;
+  if(mc)
+  {
+    if((rc = ensure_buffer(s, &s->d_C, &s->cap_C, cnt(pb->C_stride), mc * n)) != JRLQP_OK) return rc;
+    if((rc = ensure_buffer(s, &s->d_bl, &s->cap_bl, cnt(pb->bl_stride), mc)) != JRLQP_OK) return rc;
+    if((rc = ensure_buffer(s, &s->d_bu, &s->cap_bu, cnt(pb->bu_stride), mc)) != JRLQP_OK) return rc;
+  }
+  if(s->nb)
+  {
+    if((rc = ensure_buffer(s, &s->d_xl, &s->cap_xl, cnt(pb->xl_stride), n)) != JRLQP_OK) return rc;
+    if((rc = ensure_buffer(s, &s->d_xu, &s->cap_xu, cnt(pb->xu_stride), n)) != JRLQP_OK) return rc;
+  }
   if(!s->staging_ready)
   {
-    CK(cudaMalloc(&s->d_G, sizeof(double) * B * n * n));
-    CK(cudaMalloc(&s->d_a, sizeof(double) * B * n));
-    if(mc)
-    {
-      CK(cudaMalloc(&s->d_C, sizeof(double) * B * mc * n));
-      CK(cudaMalloc(&s->d_bl, sizeof(double) * B * mc));
-      CK(cudaMalloc(&s->d_bu, sizeof(double) * B * mc));
-    }
-    if(s->nb)
-    {
-      CK(cudaMalloc(&s->d_xl, sizeof(double) * B * n));
-      CK(cudaMalloc(&s->d_xu, sizeof(double) * B * n));
-    }
     CK(cudaMalloc(&s->d_x, sizeof(double) * B * n));
     CK(cudaMalloc(&s->d_u, sizeof(double) * B * std::max<long long>(m, 1)));
     CK(cudaMalloc(&s->d_f, sizeof(double) * B));
@@ -580,7 +687,7 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
   if(pb->batch > s->capacity) return JRLQP_ERR_CAPACITY;
   if(pb->batch == 0) return JRLQP_SUCCESS;
   CK(cudaSetDevice(s->device));
-  rc = ensure_staging(s, res->L != nullptr);
+  rc = ensure_staging(s, pb, res->L != nullptr);
   if(rc != JRLQP_OK) return rc;
 
   const long long B = pb->batch;
@@ -592,6 +699,36 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
   long long nchunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (B + chunk - 1) / chunk));
   chunk = (B + nchunks - 1) / nchunks;
 
+  // arrays shared by the batch (stride 0): uploaded once, on stream 0; the other streams wait for them
+  {
+    bool any = false;
+    auto up1 = [&](double * d, const double * h, long long hstride, int rows, int cols, int ld) -> cudaError_t
+    {
+      if(hstride != 0 || !h) return cudaSuccess;
+      any = true;
+      return h2d(d, h, 0, 1, rows, cols, ld, s->streams[0]);
+    };
+    CK(up1(s->d_G, pb->G, pb->G_stride, (int)n, (int)n, pb->ldg));
+    CK(up1(s->d_a, pb->a, pb->a_stride, (int)n, 1, (int)n));
+    if(mc)
+    {
+      CK(up1(s->d_C, pb->C, pb->C_stride, (int)n, (int)mc, pb->ldc));
+      CK(up1(s->d_bl, pb->bl, pb->bl_stride, (int)mc, 1, (int)mc));
+      CK(up1(s->d_bu, pb->bu, pb->bu_stride, (int)mc, 1, (int)mc));
+    }
+    if(s->nb)
+    {
+      CK(up1(s->d_xl, pb->xl, pb->xl_stride, (int)n, 1, (int)n));
+      CK(up1(s->d_xu, pb->xu, pb->xu_stride, (int)n, 1, (int)n));
+    }
+    if(any)
+    {
+      if(!s->ev_shared) CK(cudaEventCreateWithFlags(&s->ev_shared, cudaEventDisableTiming));
+      CK(cudaEventRecord(s->ev_shared, s->streams[0]));
+      for(int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(s->streams[i], s->ev_shared, 0));
+    }
+  }
+
   for(long long c = 0; c < nchunks; ++c)
   {
     const long long b0 = c * chunk;
@@ -600,13 +737,18 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
     cudaStream_t st = s->streams[c % kStreams];
     jrlqp_problem dp{};
     dp.batch = cnt;
-    // shared (stride 0) arrays are uploaded by every chunk into slot b0 (tiny, keeps chunks independent)
     auto up = [&](double * dbase, const double * h, long long hstride, int rows, int cols, int ld, const double *& dptr, int64_t & dstride) -> cudaError_t
     {
       const long long blk = (long long)rows * cols;
+      if(hstride == 0)
+      {
+        dptr = dbase; // uploaded above
+        dstride = 0;
+        return cudaSuccess;
+      }
       double * d = dbase + b0 * blk;
       dptr = d;
-      dstride = hstride == 0 ? 0 : blk;
+      dstride = blk;
       return h2d(d, h + b0 * hstride, hstride, cnt, rows, cols, ld, st);
     };
     CK(up(s->d_G, pb->G, pb->G_stride, (int)n, (int)n, pb->ldg, dp.G, dp.G_stride));

@@ -192,6 +192,140 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
   return (c0 + c1) + (c2 + c3);
 }
 
+// Givens recurrence for the sweep i = n-2 .. q (the constraint would become the (q+1)-th).
+// Serial part: rho_i = r(d[i], rho_{i+1}) — one division and one square root per link, exactly the
+// operations of Eigen's makeGivens that feed r. The rest of makeGivens (second division, products)
+// does not feed the recurrence: it is evaluated afterwards, one rotation per lane.
+// Free function (one warp, lane = threadIdx.x & 31) shared by the shared-memory kernel and the
+// global-workspace kernel (gi_large.cuh).
+__device__ __forceinline__ void givens_chain(const int q, const int n, const int lane, const double * ds, double2 * gcs, double * gc, double * gs, int * gk, double * scr)
+{
+  // Latency of one link is what matters here. Per link, Eigen's makeGivens needs t = num / den,
+  // u = sqrt(1 + t^2), r = den u, with den = rho (the running value) in the common case
+  // |rho| >= |p|. The stock division and square root chain ~20 dependent FP64 operations; here
+  //  * a reciprocal of rho is carried along the recurrence (rr0 = |1/rho| * y1, y1 ~ 1/sqrt(1+t^2)
+  //    being a by-product of the square root), so that t costs 2 dependent FMAs after rho is known
+  //    (div_rcp with the product q0 = p * rr0 issued one link ahead), and is PROVEN to be the
+  //    correctly rounded quotient by an exact remainder test off the chain (see fp64_exact.cuh);
+  //  * every other case (|d[i]| > |rho|, a zero operand, proof declined) leaves the straight-line
+  //    fast path through one branch and is evaluated with precomputed 1 / d[i] or literally.
+  double * rpv = reinterpret_cast<double *>(gcs); // 1 / d[i]; gcs is only written after the chain
+#pragma unroll 1
+  for(int i = q + lane; i <= n - 1; i += 32) rpv[i] = 1.0 / ds[i];
+  __syncwarp();
+  double rho = ds[n - 1];
+  double rrR = rpv[n - 1]; // reciprocal of rho, refined
+  double rrE = rrR; // reciprocal of rho available before rho itself (feeds q0 and the correction)
+  int i = n - 2;
+  double p = ds[max(i, 0)];
+  double q0s = p * rrE; // first product of the quotient p / rho, issued ahead
+#pragma unroll 2
+  for(; i >= q; --i)
+  {
+    const double pn = ds[max(i - 1, 0)]; // operand of the next link
+    // ---- fast path: t = p / rho, straight line
+    const double e3 = fma(-rho, q0s, p);
+    double a = fma(e3, rrE, q0s);
+    const double e2 = fma(-rho, a, p); // exact remainder (proof)
+    double y1;
+    const double us = sqrt_rsqrt(fma(a, a, 1.0), y1);
+    double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
+    double rr0 = fabs(rrR) * y1; // ~ 1 / r, known before r
+    double rrn = fma(rr0, fma(-r, rr0, 1.0), rr0);
+    double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
+    int kind = 3;
+    // proof that a == RN(p / rho): |e2| < |rho| ulp(a) / 2, a not a power of two, nothing near underflow
+    const int ahi = __double2hiint(a);
+    const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
+    const double tol = fabs(rho) * hu;
+    const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
+    const bool fast = fabs(e2) < tol && tol > 1e-270 && !pow2 && fabs(p) <= fabs(rho) && p != 0.0;
+    if(!fast)
+    {
+      const double rp = rpv[i];
+      if(rho == 0.0)
+      {
+        kind = 0;
+        a = p;
+        u = 1.0;
+        r = fabs(p);
+        rr0 = fabs(rp);
+      }
+      else if(p == 0.0)
+      {
+        kind = 1;
+        a = rho;
+        u = 1.0;
+        r = fabs(rho);
+        rr0 = fabs(rrR);
+      }
+      else
+      {
+        const bool pg = fabs(p) > fabs(rho);
+        kind = pg ? 2 : 3;
+        const double num = pg ? rho : p, den = pg ? p : rho;
+        bool ok = false;
+        if(pg) a = div_rcp(num, den, rp, ok); // 1 / p was precomputed
+        if(!ok) a = num / den;
+        const double uu = sqrt(fma(a, a, 1.0));
+        u = den < 0.0 ? -uu : uu;
+        r = den * u;
+        rr0 = 1.0 / r;
+      }
+      rrn = rr0;
+    }
+    if(lane == 0)
+    {
+      // stash (t, u) and what the trivial branches need
+      gc[i] = a;
+      gs[i] = u;
+      gk[i] = kind;
+    }
+    rho = r;
+    rrR = rrn;
+    rrE = rr0;
+    p = pn;
+    q0s = pn * rr0;
+  }
+  if(lane == 0) scr[11] = rrR; // ~ 1 / rho: reciprocal of the new diagonal entry of R
+  if(lane == 0) scr[10] = rho;
+  __syncwarp();
+#pragma unroll 1
+  for(int i = q + lane; i <= n - 2; i += 32)
+  {
+    const int kind = gk[i];
+    const double a = gc[i];
+    double c, sn;
+    if(kind == 0)
+    {
+      c = a < 0.0 ? -1.0 : 1.0;
+      sn = 0.0;
+    }
+    else if(kind == 1)
+    {
+      c = 0.0;
+      sn = a < 0.0 ? 1.0 : -1.0;
+    }
+    else
+    {
+      // kind 2: c = 1/u, s = -t c ; kind 3: s = -1/u, c = -t s  (-1/u == -(1/u) exactly)
+      const double inv = 1.0 / gs[i];
+      if(kind == 2)
+      {
+        c = inv;
+        sn = -a * c;
+      }
+      else
+      {
+        sn = -inv;
+        c = -a * sn;
+      }
+    }
+    gcs[i] = make_double2(c, sn);
+  }
+
+}
+
 struct Sel
 {
   int p;
@@ -1299,136 +1433,8 @@ struct GiCta
       if(lane + 32 * s < q) rs[lane + 32 * s] = rr[s];
   }
 
-  // Givens recurrence for the sweep i = n-2 .. q (the constraint would become the (q+1)-th).
-  // Serial part: rho_i = r(d[i], rho_{i+1}) — one division and one square root per link, exactly the
-  // operations of Eigen's makeGivens that feed r. The rest of makeGivens (second division, products)
-  // does not feed the recurrence: it is evaluated afterwards, one rotation per lane.
-  __device__ __forceinline__ void givens_recurrence()
-  {
-    // Latency of one link is what matters here. Per link, Eigen's makeGivens needs t = num / den,
-    // u = sqrt(1 + t^2), r = den u, with den = rho (the running value) in the common case
-    // |rho| >= |p|. The stock division and square root chain ~20 dependent FP64 operations; here
-    //  * a reciprocal of rho is carried along the recurrence (rr0 = |1/rho| * y1, y1 ~ 1/sqrt(1+t^2)
-    //    being a by-product of the square root), so that t costs 2 dependent FMAs after rho is known
-    //    (div_rcp with the product q0 = p * rr0 issued one link ahead), and is PROVEN to be the
-    //    correctly rounded quotient by an exact remainder test off the chain (see fp64_exact.cuh);
-    //  * every other case (|d[i]| > |rho|, a zero operand, proof declined) leaves the straight-line
-    //    fast path through one branch and is evaluated with precomputed 1 / d[i] or literally.
-    double * rpv = reinterpret_cast<double *>(gcs); // 1 / d[i]; gcs is only written after the chain
-#pragma unroll 1
-    for(int i = q + lane; i <= n - 1; i += 32) rpv[i] = 1.0 / ds[i];
-    __syncwarp();
-    double rho = ds[n - 1];
-    double rrR = rpv[n - 1]; // reciprocal of rho, refined
-    double rrE = rrR; // reciprocal of rho available before rho itself (feeds q0 and the correction)
-    int i = n - 2;
-    double p = ds[max(i, 0)];
-    double q0s = p * rrE; // first product of the quotient p / rho, issued ahead
-#pragma unroll 2
-    for(; i >= q; --i)
-    {
-      const double pn = ds[max(i - 1, 0)]; // operand of the next link
-      // ---- fast path: t = p / rho, straight line
-      const double e3 = fma(-rho, q0s, p);
-      double a = fma(e3, rrE, q0s);
-      const double e2 = fma(-rho, a, p); // exact remainder (proof)
-      double y1;
-      const double us = sqrt_rsqrt(fma(a, a, 1.0), y1);
-      double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
-      double rr0 = fabs(rrR) * y1; // ~ 1 / r, known before r
-      double rrn = fma(rr0, fma(-r, rr0, 1.0), rr0);
-      double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
-      int kind = 3;
-      // proof that a == RN(p / rho): |e2| < |rho| ulp(a) / 2, a not a power of two, nothing near underflow
-      const int ahi = __double2hiint(a);
-      const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
-      const double tol = fabs(rho) * hu;
-      const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
-      const bool fast = fabs(e2) < tol && tol > 1e-270 && !pow2 && fabs(p) <= fabs(rho) && p != 0.0;
-      if(!fast)
-      {
-        const double rp = rpv[i];
-        if(rho == 0.0)
-        {
-          kind = 0;
-          a = p;
-          u = 1.0;
-          r = fabs(p);
-          rr0 = fabs(rp);
-        }
-        else if(p == 0.0)
-        {
-          kind = 1;
-          a = rho;
-          u = 1.0;
-          r = fabs(rho);
-          rr0 = fabs(rrR);
-        }
-        else
-        {
-          const bool pg = fabs(p) > fabs(rho);
-          kind = pg ? 2 : 3;
-          const double num = pg ? rho : p, den = pg ? p : rho;
-          bool ok = false;
-          if(pg) a = div_rcp(num, den, rp, ok); // 1 / p was precomputed
-          if(!ok) a = num / den;
-          const double uu = sqrt(fma(a, a, 1.0));
-          u = den < 0.0 ? -uu : uu;
-          r = den * u;
-          rr0 = 1.0 / r;
-        }
-        rrn = rr0;
-      }
-      if(lane == 0)
-      {
-        // stash (t, u) and what the trivial branches need
-        gc[i] = a;
-        gs[i] = u;
-        gk[i] = kind;
-      }
-      rho = r;
-      rrR = rrn;
-      rrE = rr0;
-      p = pn;
-      q0s = pn * rr0;
-    }
-    if(lane == 0) scr[11] = rrR; // ~ 1 / rho: reciprocal of the new diagonal entry of R
-    if(lane == 0) scr[10] = rho;
-    __syncwarp();
-#pragma unroll 1
-    for(int i = q + lane; i <= n - 2; i += 32)
-    {
-      const int kind = gk[i];
-      const double a = gc[i];
-      double c, sn;
-      if(kind == 0)
-      {
-        c = a < 0.0 ? -1.0 : 1.0;
-        sn = 0.0;
-      }
-      else if(kind == 1)
-      {
-        c = 0.0;
-        sn = a < 0.0 ? 1.0 : -1.0;
-      }
-      else
-      {
-        // kind 2: c = 1/u, s = -t c ; kind 3: s = -1/u, c = -t s  (-1/u == -(1/u) exactly)
-        const double inv = 1.0 / gs[i];
-        if(kind == 2)
-        {
-          c = inv;
-          sn = -a * c;
-        }
-        else
-        {
-          sn = -inv;
-          c = -a * sn;
-        }
-      }
-      gcs[i] = make_double2(c, sn);
-    }
-  }
+  // Givens recurrence of the add that may follow (see givens_chain above)
+  __device__ __forceinline__ void givens_recurrence() { givens_chain(q, n, lane, ds, gcs, gc, gs, gk, scr); }
 
   // ------------------------------------------------------------------------------------------
   // computeStepLength_ (src/GoldfarbIdnaniSolver.cpp:150-219), incl. the activationStatus(k) quirk.

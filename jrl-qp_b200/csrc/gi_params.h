@@ -65,6 +65,11 @@ struct GiParams
   int * active_list;
   int * n_active;
   double * L;
+  // global-memory workspace of the large-n kernel (gi_large.cuh): one slice of work_stride doubles per CTA
+  double * work;
+  long long work_stride;
+  int * work_busy; // one flag per slice: a CTA claims a free slice when it starts and releases it when it exits
+  int work_slots;
   // persistent work queue
   unsigned long long * counter;
   unsigned long long * phase_cycles; // [4 warps][16 phases], only with -DJRLQP_PHASE_TIMING (else null)

@@ -67,7 +67,7 @@ class ProblemBatch:
 
     @property
     def mc(self):
-        return self.bl.shape[1]
+        return 0 if self.bl is None else self.bl.shape[-1]  # bl may be shared by the batch (1-D)
 
     @property
     def nb(self):

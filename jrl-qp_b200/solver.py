@@ -109,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "jrlqp_structured_create", "jrlqp_structured_destroy", "jrlqp_structured_last_error",
     "jrlqp_structured_llt_device", "jrlqp_structured_llt_host", "jrlqp_structured_solve_device",
     "jrlqp_structured_solve_host", "jrlqp_structured_get_info", "jrlqp_selftest_arith",
-    "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host",
+    "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host", "jrlqp_set_kernel_path",
 ]
 
 _lib = None
@@ -136,6 +136,7 @@ def load_library():
         lib.jrlqp_set_options.argtypes = [C.c_void_p, C.POINTER(_Options)]
         lib.jrlqp_get_kernel_info.argtypes = [C.c_void_p, C.POINTER(KernelInfo)]
         lib.jrlqp_set_stage_c.argtypes = [C.c_void_p, C.c_int32]
+        lib.jrlqp_set_kernel_path.argtypes = [C.c_void_p, C.c_int32]
         lib.jrlqp_solve_batch_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
         lib.jrlqp_solve_batch_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
         lib.jrlqp_solve_batch_warm_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
@@ -237,6 +238,13 @@ class BatchedGoldfarbIdnaniSolver:
         rc = self._lib.jrlqp_set_stage_c(self._h, int(mode))
         if rc != 0:
             raise JrlQpError(f"jrlqp_set_stage_c failed: {self._lib.jrlqp_last_error(self._h).decode()}")
+
+    def set_kernel_path(self, mode):
+        """0 automatic, 1 shared-memory kernel (n <= 128), 2 global-workspace kernel (any n <= 1024)."""
+        rc = self._lib.jrlqp_set_kernel_path(self._h, int(mode))
+        if rc != 0:
+            raise JrlQpError(f"jrlqp_set_kernel_path failed: {self._lib.jrlqp_last_error(self._h).decode()}")
+        return self
 
     def _problem(self, B, G, a, Cm, bl, bu, xl, xu, shared, ldg=None, ldc=None):
         n, mc = self.n, self.mc
