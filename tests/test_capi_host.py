@@ -56,7 +56,7 @@ def test_invalid_arguments_are_rejected():
     lib = S.load_library()
     h = C.c_void_p()
     assert lib.jrlqp_create(C.byref(h), 0, 1, 0, 1, 0) == -2  # JRLQP_ERR_ARG
-    assert lib.jrlqp_create(C.byref(h), 129, 1, 0, 1, 0) == -2
+    assert lib.jrlqp_create(C.byref(h), 1025, 1, 0, 1, 0) == -2
     assert lib.jrlqp_create(None, 5, 1, 0, 1, 0) == -2
 
 
