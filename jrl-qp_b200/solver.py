@@ -309,15 +309,21 @@ class BatchedGoldfarbIdnaniSolver:
 
     def solve_device(self, B, G, a, Cm, bl, bu, xl, xu, x, u=None, f=None, iterations=None, status=None,
                      active_set=None, active_list=None, n_active=None, L=None, stream=0, shared=(), ldg=None, ldc=None,
-                     strides=None):
+                     strides=None, experimental=False, as_in=None, as_shared=False):
         """DEVICE pointers (ints or torch CUDA tensors); asynchronous on `stream` (cudaStream_t as int).
-        `shared` names arrays with stride 0; `strides` overrides element strides, e.g. {"G": n * ldg}."""
+        `shared` names arrays with stride 0; `strides` overrides element strides, e.g. {"G": n * ldg}.
+        experimental=True: the warm-start capable solver, as_in = device int8 [B, mc+nb] guess (or shared)."""
         pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, set(shared), ldg, ldc)
         for k, v in (strides or {}).items():
             setattr(pb, k + "_stride", int(v))
         res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(iterations), _ptr(status), _ptr(active_set),
                       _ptr(active_list), _ptr(n_active), _ptr(L))
-        rc = self._lib.jrlqp_solve_batch_device(self._h, C.byref(pb), C.byref(res), C.c_void_p(stream))
+        if experimental:
+            if as_in is not None:
+                pb.as_in, pb.as_stride = _ptr(as_in), (0 if as_shared else self.m)
+            rc = self._lib.jrlqp_solve_batch_warm_device(self._h, C.byref(pb), C.byref(res), C.c_void_p(stream))
+        else:
+            rc = self._lib.jrlqp_solve_batch_device(self._h, C.byref(pb), C.byref(res), C.c_void_p(stream))
         if rc != 0:
             raise JrlQpError(f"jrlqp_solve_batch_device failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
 
