@@ -215,6 +215,73 @@ double jrlqp_measure_fp64_tflops(int32_t device, int32_t repeats);
 int jrlqp_selftest_arith(int32_t device, int64_t samples, uint64_t seed, int32_t exponent_span, int32_t rcp_ulps, uint64_t * counts5);
 
 /* ------------------------------------------------------------------------------------------------
+ * Warm-started SEQUENCES: the reference's control-loop use case and benchmark
+ * (benchmarks/SolversWarmStart.cpp:234-276): the same G, C and bounds are solved `steps` times with a
+ * slowly varying linear term a(t); with warm != 0 every step after the first is warm-started from the
+ * active set the previous step ended with ("as empty => reuse the previous active set",
+ * src/experimental/GoldfarbIdnaniSolver.cpp:58-61), the first one from pb->as_in (nullable), through the
+ * experimental solver (BENCH_GI_EX); with warm == 0 every step is a cold solve of the stable solver
+ * (BENCH_GI). The whole sequence is enqueued on one stream: the active set never leaves the GPU.
+ *   pb->a               linear term of step 0; step t reads pb->a + t * a_step_stride (elements)
+ *   res                 outputs of the LAST step — unless a *_step_stride below is non-zero, in which
+ *                       case step t writes that output at (pointer + t * stride) (elements)
+ *   iterations_total    [batch] (nullable) sum of iterations() over the steps — the "it" counter of the
+ *                       reference benchmark
+ *   status_worst        [batch] (nullable) worst TerminationStatus over the steps
+ * res->active_set is required when warm != 0 (it carries the active set from step to step).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct jrlqp_sequence
+{
+  int32_t steps;
+  int32_t warm;
+  int64_t a_step_stride;
+  int64_t x_step_stride; /* 0: only the last step's solution is kept */
+  int64_t u_step_stride;
+  int64_t f_step_stride;
+  int64_t iterations_step_stride;
+  int64_t status_step_stride;
+  int32_t * iterations_total;
+  int32_t * status_worst;
+} jrlqp_sequence;
+/* DEVICE pointers, asynchronous on `stream`. */
+int jrlqp_solve_sequence_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_sequence * seq, const jrlqp_result * res, void * stream);
+/* HOST pointers: G, C, bounds and all `steps` linear terms are uploaded once, the steps run back to back
+ * on the device, the requested outputs come back once. Returns the worst status over batch and steps
+ * (>= 0) or a negative JRLQP_ERR_*. */
+int jrlqp_solve_sequence_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_sequence * seq, const jrlqp_result * res);
+
+/* ------------------------------------------------------------------------------------------------
+ * GPU-side batch verifier: jrl::qp::test::testKKT (src/test/kkt.cpp:87-195:
+ * stationarity |G x + a + C u_c + u_b|_inf <= tau_d (1 + |u|_inf), and per constraint one of
+ * {at lower & u <= -tau_u, inside & |u| <= tau_u, at upper & u >= tau_u} with tau_x = tau_p (1 + |x|_inf))
+ * and the planted-solution comparison of the reference's tests (x.isApprox(x_ref, prec),
+ * tests/GoldfarbIdnaniSolverTest.cpp:94-97), for a batch resident in HBM. Uses the FULL matrix G
+ * (both triangles), as the reference does.
+ *   flags  [batch]     bit 0: stationarity holds, bit 1: feasibility / complementarity holds,
+ *                      bit 2: x ~ x_ref (only when x_ref is given)
+ *   resid  [batch][4]  (nullable) |dL|_inf, tau_u, tau_x, |x - x_ref|^2
+ *   n_fail             (nullable) number of instances with a missing bit. _device: a DEVICE counter the
+ *                      caller has zeroed; _host: a host int64.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct jrlqp_kkt_args
+{
+  int32_t n, mc, use_bounds;
+  double tau_p, tau_d; /* 1e-6, 1e-6 (include/jrl-qp/test/kkt.h:83-84) */
+  double prec; /* 1e-6 */
+  const double * x; /* [batch][n] */
+  const double * u; /* [batch][mc+nb], reference sign convention (DualSolver::multipliers) */
+  const double * x_ref; /* [batch][n], nullable */
+  int32_t * flags;
+  double * resid;
+  int64_t * n_fail;
+} jrlqp_kkt_args;
+void jrlqp_kkt_default_args(jrlqp_kkt_args * k);
+int jrlqp_kkt_check_device(const jrlqp_problem * pb, const jrlqp_kkt_args * k, int32_t device, void * stream);
+/* Host pointers (uploads the batch; a verifier, not a hot path). Returns the number of failing
+ * instances (>= 0, saturating) or a negative JRLQP_ERR_*. */
+int jrlqp_kkt_check_host(const jrlqp_problem * pb, const jrlqp_kkt_args * k, int32_t device);
+
+/* ------------------------------------------------------------------------------------------------
  * Structured Cholesky decompositions (north-star item 4), batched: `batch` matrices that share ONE
  * block structure are factorised / solved by one call, one instance per CTA.
  *

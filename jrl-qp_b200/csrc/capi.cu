@@ -159,6 +159,13 @@ struct jrlqp_solver
   int wsmem_bytes = 0;
   int wocc = 0;
   signed char * d_as = nullptr; // staging of as_in for the host entry point
+  // warm-started sequences (jrlqp_solve_sequence_*): scratch for per-step iterations / status and host staging
+  int * d_seq_it = nullptr;
+  int * d_seq_status = nullptr;
+  long long cap_seq = 0;
+  double * d_seq = nullptr; // arena: linear terms of all steps + per-step outputs (host entry point)
+  long long cap_seq_arena = 0;
+  int * d_seq_tot = nullptr; // [2][capacity]: iterations_total, status_worst (host entry point)
   // large-n kernel (gi_large.cuh): J, L and R live in a per-CTA global-memory workspace
   int path_mode = 0; // 0 automatic (n <= 128: shared-memory kernel), 1 shared-memory kernel, 2 global-workspace kernel
   bool large = false;
@@ -378,7 +385,7 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -470,7 +477,7 @@ static int validate(const jrlqp_solver * s, const jrlqp_problem * pb, const jrlq
 
 static int configure_warm(jrlqp_solver * s);
 
-static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter, bool warm = false)
+static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter, bool warm = false, bool force_warm_start = false)
 {
   if(s->large)
   {
@@ -508,7 +515,7 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.sxu = pb->xu_stride;
   p.as_in = warm ? reinterpret_cast<const signed char *>(pb->as_in) : nullptr;
   p.s_as = pb->as_stride;
-  p.warm_start = warm ? s->opt.warm_start : 0;
+  p.warm_start = warm ? (force_warm_start ? 1 : s->opt.warm_start) : 0;
   p.x = res->x;
   p.u = res->u;
   p.f = res->f;
@@ -825,6 +832,214 @@ int jrlqp_solve_batch_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrl
 int jrlqp_solve_batch_warm_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res)
 {
   return solve_batch_host_impl(s, pb, res, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warm-started sequences (benchmarks/SolversWarmStart.cpp:234-276)
+// ---------------------------------------------------------------------------------------------
+__global__ void seq_accumulate_kernel(const int * __restrict__ it, const int * __restrict__ status, int * it_total, int * status_worst, long long batch, int first)
+{
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if(b >= batch) return;
+  if(it_total) it_total[b] = (first ? 0 : it_total[b]) + it[b];
+  if(status_worst) status_worst[b] = first ? status[b] : max(status_worst[b], status[b]);
+}
+
+static int validate_sequence(const jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_sequence * seq, const jrlqp_result * res, bool device)
+{
+  int rc = validate(s, pb, res);
+  if(rc != JRLQP_OK) return rc;
+  if(!seq || seq->steps < 1) return JRLQP_ERR_ARG;
+  if(device && seq->warm && !res->active_set) return JRLQP_ERR_ARG; // carries the active set from step to step
+  return JRLQP_OK;
+}
+
+static int sequence_device_impl(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_sequence * seq, const jrlqp_result * res, cudaStream_t st)
+{
+  const long long B = pb->batch;
+  const bool totals = seq->iterations_total || seq->status_worst;
+  if(totals && (!res->iterations || !res->status) && B > s->cap_seq)
+  {
+    if(s->d_seq_it) CK(cudaFree(s->d_seq_it));
+    if(s->d_seq_status) CK(cudaFree(s->d_seq_status));
+    s->d_seq_it = s->d_seq_status = nullptr;
+    s->cap_seq = 0;
+    CK(cudaMalloc(&s->d_seq_it, sizeof(int) * (size_t)B));
+    CK(cudaMalloc(&s->d_seq_status, sizeof(int) * (size_t)B));
+    s->cap_seq = B;
+  }
+  unsigned long long * counter = s->d_counters + (s->next_counter++ % kMaxChunks);
+  for(int t = 0; t < seq->steps; ++t)
+  {
+    jrlqp_problem p = *pb;
+    p.a = pb->a + (long long)t * seq->a_step_stride;
+    jrlqp_result r = *res;
+    r.x = res->x + (long long)t * seq->x_step_stride;
+    if(res->u) r.u = res->u + (long long)t * seq->u_step_stride;
+    if(res->f) r.f = res->f + (long long)t * seq->f_step_stride;
+    if(res->iterations) r.iterations = res->iterations + (long long)t * seq->iterations_step_stride;
+    if(res->status) r.status = res->status + (long long)t * seq->status_step_stride;
+    if(totals)
+    {
+      if(!r.iterations) r.iterations = s->d_seq_it;
+      if(!r.status) r.status = s->d_seq_status;
+    }
+    if(seq->warm && t > 0)
+    {
+      // the active set the previous step ended with, read in place: an instance reads its guess
+      // when it starts and writes its final set when it ends, and no other CTA touches that row
+      p.as_in = res->active_set;
+      p.as_stride = s->m;
+    }
+    int rc = launch(s, &p, &r, st, counter, seq->warm != 0, seq->warm != 0);
+    if(rc != JRLQP_OK) return rc;
+    if(totals)
+    {
+      const unsigned grid = (unsigned)((B + 255) / 256);
+      seq_accumulate_kernel<<<grid, 256, 0, st>>>(r.iterations, r.status, seq->iterations_total, seq->status_worst, B, t == 0);
+      g_launches.fetch_add(1);
+      CK(cudaGetLastError());
+    }
+  }
+  return JRLQP_OK;
+}
+
+int jrlqp_solve_sequence_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_sequence * seq, const jrlqp_result * res, void * stream)
+{
+  int rc = validate_sequence(s, pb, seq, res, true);
+  if(rc != JRLQP_OK) return rc;
+  if(pb->batch == 0) return JRLQP_OK;
+  CK(cudaSetDevice(s->device));
+  return sequence_device_impl(s, pb, seq, res, (cudaStream_t)stream);
+}
+
+int jrlqp_solve_sequence_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_sequence * seq, const jrlqp_result * res)
+{
+  int rc = validate_sequence(s, pb, seq, res, false);
+  if(rc != JRLQP_OK) return rc;
+  if(pb->batch > s->capacity) return JRLQP_ERR_CAPACITY;
+  if(pb->batch == 0) return JRLQP_SUCCESS;
+  if(res->L) return JRLQP_ERR_ARG; // the factor does not change along a sequence: ask one plain solve for it
+  CK(cudaSetDevice(s->device));
+  rc = ensure_staging(s, pb, false);
+  if(rc != JRLQP_OK) return rc;
+  const long long B = pb->batch, n = s->n, mc = s->mc, m = s->m, T = seq->steps;
+  cudaStream_t st = s->streams[0];
+  // arena: [T][B][n] linear terms, then the per-step outputs that were asked for
+  const long long na = T * B * n;
+  const long long nx = seq->x_step_stride ? T * B * n : 0;
+  const long long nu = (res->u && seq->u_step_stride) ? T * B * std::max<long long>(m, 1) : 0;
+  const long long nf = (res->f && seq->f_step_stride) ? T * B : 0;
+  const long long ni = (res->iterations && seq->iterations_step_stride) ? (T * B + 1) / 2 : 0; // ints, packed in doubles
+  const long long ns = (res->status && seq->status_step_stride) ? (T * B + 1) / 2 : 0;
+  const long long need = na + nx + nu + nf + ni + ns;
+  if(need > s->cap_seq_arena)
+  {
+    if(s->d_seq) CK(cudaFree(s->d_seq));
+    s->d_seq = nullptr;
+    s->cap_seq_arena = 0;
+    CK(cudaMalloc(&s->d_seq, sizeof(double) * (size_t)need));
+    s->cap_seq_arena = need;
+  }
+  if(!s->d_seq_tot) CK(cudaMalloc(&s->d_seq_tot, sizeof(int) * 2 * (size_t)std::max<long long>(s->capacity, 1)));
+  double * d_aseq = s->d_seq;
+  double * d_xs = d_aseq + na;
+  double * d_us = d_xs + nx;
+  double * d_fs = d_us + nu;
+  int * d_is = reinterpret_cast<int *>(d_fs + nf);
+  int * d_ss = reinterpret_cast<int *>(d_fs + nf + ni);
+
+  jrlqp_problem dp{};
+  dp.batch = B;
+  auto up = [&](double * d, const double * h, long long hstride, int rows, int cols, int ld, const double *& dptr, int64_t & dstride) -> cudaError_t
+  {
+    dptr = d;
+    dstride = hstride == 0 ? 0 : (long long)rows * cols;
+    return h2d(d, h, hstride, B, rows, cols, ld, st);
+  };
+  CK(up(s->d_G, pb->G, pb->G_stride, (int)n, (int)n, pb->ldg, dp.G, dp.G_stride));
+  dp.ldg = (int)n;
+  dp.ldc = (int)n;
+  if(mc)
+  {
+    CK(up(s->d_C, pb->C, pb->C_stride, (int)n, (int)mc, pb->ldc, dp.C, dp.C_stride));
+    CK(up(s->d_bl, pb->bl, pb->bl_stride, (int)mc, 1, (int)mc, dp.bl, dp.bl_stride));
+    CK(up(s->d_bu, pb->bu, pb->bu_stride, (int)mc, 1, (int)mc, dp.bu, dp.bu_stride));
+  }
+  if(s->nb)
+  {
+    CK(up(s->d_xl, pb->xl, pb->xl_stride, (int)n, 1, (int)n, dp.xl, dp.xl_stride));
+    CK(up(s->d_xu, pb->xu, pb->xu_stride, (int)n, 1, (int)n, dp.xu, dp.xu_stride));
+  }
+  // linear terms: step t, instance b at a + t * a_step_stride + b * a_stride  ->  dense [T][B][n]
+  for(long long t = 0; t < T; ++t)
+  {
+    const double * h = pb->a + t * seq->a_step_stride;
+    if(pb->a_stride == 0)
+      for(long long b = 0; b < B; ++b) CK(cudaMemcpyAsync(d_aseq + (t * B + b) * n, h, sizeof(double) * n, cudaMemcpyHostToDevice, st)); // shared within a step (rare)
+    else
+      CK(h2d(d_aseq + t * B * n, h, pb->a_stride, B, (int)n, 1, (int)n, st));
+  }
+  dp.a = d_aseq;
+  dp.a_stride = n;
+  if(seq->warm && pb->as_in)
+  {
+    if(!s->d_as) CK(cudaMalloc(&s->d_as, std::max<long long>(std::max<long long>(s->capacity, 1) * m, 1)));
+    const long long cnt_as = pb->as_stride == 0 ? 1 : B;
+    if(pb->as_stride == m || cnt_as == 1)
+      CK(cudaMemcpyAsync(s->d_as, pb->as_in, (size_t)(cnt_as * m), cudaMemcpyHostToDevice, st));
+    else
+      CK(cudaMemcpy2DAsync(s->d_as, (size_t)m, pb->as_in, (size_t)pb->as_stride, (size_t)m, (size_t)cnt_as, cudaMemcpyHostToDevice, st));
+    dp.as_in = reinterpret_cast<const int8_t *>(s->d_as);
+    dp.as_stride = pb->as_stride == 0 ? 0 : m;
+  }
+  jrlqp_sequence ds = *seq;
+  ds.a_step_stride = B * n;
+  ds.x_step_stride = nx ? B * n : 0;
+  ds.u_step_stride = nu ? B * m : 0;
+  ds.f_step_stride = nf ? B : 0;
+  ds.iterations_step_stride = ni ? B : 0;
+  ds.status_step_stride = ns ? B : 0;
+  ds.iterations_total = s->d_seq_tot;
+  ds.status_worst = s->d_seq_tot + std::max<long long>(s->capacity, 1);
+  jrlqp_result dr{};
+  dr.x = nx ? d_xs : s->d_x;
+  dr.u = res->u ? (nu ? d_us : s->d_u) : nullptr;
+  dr.f = res->f ? (nf ? d_fs : s->d_f) : nullptr;
+  dr.iterations = res->iterations ? (ni ? d_is : s->d_it) : nullptr;
+  dr.status = res->status ? (ns ? d_ss : s->d_status) : nullptr;
+  dr.active_set = (res->active_set || seq->warm) ? s->d_act : nullptr;
+  dr.active_list = res->active_list ? s->d_alist : nullptr;
+  dr.n_active = res->n_active ? s->d_nact : nullptr;
+  rc = sequence_device_impl(s, &dp, &ds, &dr, st);
+  if(rc != JRLQP_OK) return rc;
+  // read back: per-step outputs step by step (the host strides are the caller's), the rest once
+  auto down = [&](void * h, const void * d, long long hstep, long long dstep, size_t elem, long long per) -> cudaError_t
+  {
+    const long long steps = hstep ? T : 1;
+    for(long long t = 0; t < steps; ++t)
+    {
+      cudaError_t e = cudaMemcpyAsync((char *)h + t * hstep * elem, (const char *)d + t * dstep * elem, elem * (size_t)(B * per), cudaMemcpyDeviceToHost, st);
+      if(e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  CK(down(res->x, dr.x, seq->x_step_stride, ds.x_step_stride, sizeof(double), n));
+  if(res->u && m) CK(down(res->u, dr.u, seq->u_step_stride, ds.u_step_stride, sizeof(double), m));
+  if(res->f) CK(down(res->f, dr.f, seq->f_step_stride, ds.f_step_stride, sizeof(double), 1));
+  if(res->iterations) CK(down(res->iterations, dr.iterations, seq->iterations_step_stride, ds.iterations_step_stride, sizeof(int), 1));
+  if(res->status) CK(down(res->status, dr.status, seq->status_step_stride, ds.status_step_stride, sizeof(int), 1));
+  if(res->active_set && m) CK(cudaMemcpyAsync(res->active_set, dr.active_set, (size_t)(B * m), cudaMemcpyDeviceToHost, st));
+  if(res->active_list) CK(cudaMemcpyAsync(res->active_list, dr.active_list, sizeof(int) * (size_t)(B * n), cudaMemcpyDeviceToHost, st));
+  if(res->n_active) CK(cudaMemcpyAsync(res->n_active, dr.n_active, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if(seq->iterations_total) CK(cudaMemcpyAsync(seq->iterations_total, ds.iterations_total, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  std::vector<int> worst((size_t)B);
+  CK(cudaMemcpyAsync(worst.data(), ds.status_worst, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if(seq->status_worst) std::memcpy(seq->status_worst, worst.data(), sizeof(int) * (size_t)B);
+  int w = 0;
+  for(long long b = 0; b < B; ++b) w = std::max(w, worst[(size_t)b]);
+  return w;
 }
 
 } // extern "C"

@@ -1,0 +1,360 @@
+// GPU-side batch verifier: the reference's KKT checker
+//   jrl::qp::test::testKKT = testKKTStationarity && testKKTFeasibility, checkKKTConstraint
+//   (src/test/kkt.cpp:14-195; default thresholds tau_p = tau_d = 1e-6, include/jrl-qp/test/kkt.h:83-84)
+// and the planted-solution comparison of the reference's tests (x.isApprox(pb.x, 1e-6),
+// tests/GoldfarbIdnaniSolverTest.cpp:94-97), for a whole batch that is already resident in HBM: a
+// 10^6-QP run is verified without a round trip through the host.
+//
+// One QP per CTA (T threads, persistent grid-stride loop), HBM-bound: G and C are read once from HBM
+// (C a second time from L1/L2). thread = row i for the stationarity residual
+//   dL_i = ((dot4_j(G(i,j), x_j) + a_i) [+ u_{mc+i}]) + dot4_c(C(i,c), u_c)
+// (lanes run down the columns of the column-major G and C: coalesced), thread = constraint for
+//   cx_c = dot4_i(C(i,c), x_i)  followed by checkKKTConstraint.
+// Arithmetic order = oracle/kkt_oracle.cpp, so flags AND residuals are bit-identical to the oracle.
+#include "jrlqp_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace jrlqp
+{
+void count_launch(); // capi.cu
+
+struct KktParams
+{
+  int n, mc, nb, ldg, ldc;
+  long long batch;
+  const double *G, *a, *C, *bl, *bu, *xl, *xu;
+  long long sG, sa, sC, sbl, sbu, sxl, sxu;
+  const double *x, *u, *x_ref;
+  double tau_p, tau_d, prec;
+  int * flags;
+  double * resid;
+  unsigned long long * n_fail;
+};
+
+// src/test/kkt.cpp:14-23
+__device__ __forceinline__ bool check_kkt_constraint(double cx, double bl, double bu, double u, double tau_x, double tau_u)
+{
+  const double li = cx - bl;
+  const double ui = cx - bu;
+  const bool b1 = fabs(li) <= tau_x && u <= -tau_u;
+  const bool b2 = li >= -tau_x && ui <= tau_x && fabs(u) <= tau_u;
+  const bool b3 = fabs(ui) <= tau_x && u >= tau_u;
+  return b1 || b2 || b3;
+}
+
+// dot4 of a strided vector a (stride sa) with a unit-stride shared-memory vector b
+__device__ __forceinline__ double dot4_strided(int len, const double * __restrict__ a, long long sa, const double * b)
+{
+  double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  int k = 0;
+#pragma unroll 2
+  for(; k + 3 < len; k += 4)
+  {
+    const double v0 = a[k * sa], v1 = a[(k + 1) * sa], v2 = a[(k + 2) * sa], v3 = a[(k + 3) * sa];
+    c0 = fma(v0, b[k], c0);
+    c1 = fma(v1, b[k + 1], c1);
+    c2 = fma(v2, b[k + 2], c2);
+    c3 = fma(v3, b[k + 3], c3);
+  }
+  if(k < len) c0 = fma(a[k * sa], b[k], c0);
+  if(k + 1 < len) c1 = fma(a[(k + 1) * sa], b[k + 1], c1);
+  if(k + 2 < len) c2 = fma(a[(k + 2) * sa], b[k + 2], c2);
+  return (c0 + c1) + (c2 + c3);
+}
+
+template<int T>
+__device__ __forceinline__ double block_max(double v, double * red)
+{
+#pragma unroll
+  for(int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  __syncthreads(); // red may still be read from the previous reduction
+  if((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = red[0];
+#pragma unroll
+  for(int w = 1; w < T / 32; ++w) r = fmax(r, red[w]);
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum32_kkt(double acc)
+{
+#pragma unroll
+  for(int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+  return acc;
+}
+
+template<int T>
+__global__ void __launch_bounds__(T) kkt_check_kernel(const KktParams p)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int n = p.n, mc = p.mc, nb = p.nb, m = mc + nb;
+  double * xs = sm;
+  double * us = sm + n;
+  double * red = us + m; // T / 32 entries
+  const int tid = threadIdx.x;
+  for(long long b = blockIdx.x; b < p.batch; b += gridDim.x)
+  {
+    const double * xb = p.x + b * n;
+    const double * ub = p.u + b * m;
+    double nx = 0.0, nu = 0.0;
+    for(int i = tid; i < n; i += T)
+    {
+      const double v = xb[i];
+      xs[i] = v;
+      nx = fmax(nx, fabs(v));
+    }
+    for(int i = tid; i < m; i += T)
+    {
+      const double v = ub[i];
+      us[i] = v;
+      nu = fmax(nu, fabs(v));
+    }
+    nx = block_max<T>(nx, red);
+    nu = block_max<T>(nu, red); // its barriers also publish xs / us
+    const double tau_x = p.tau_p * (1 + nx);
+    const double tau_u = p.tau_d * (1 + nu);
+
+    // stationarity (src/test/kkt.cpp:105-137), thread = row
+    const double * Gb = p.G + b * p.sG;
+    const double * ab = p.a + b * p.sa;
+    const double * Cb = mc ? p.C + b * p.sC : nullptr;
+    double mx = 0.0;
+    for(int i = tid; i < n; i += T)
+    {
+      double t = dot4_strided(n, Gb + i, p.ldg, xs) + ab[i];
+      if(nb) t = t + us[mc + i];
+      if(mc) t = t + dot4_strided(mc, Cb + i, p.ldc, us);
+      mx = fmax(mx, fabs(t));
+    }
+    const double ndL = block_max<T>(mx, red);
+
+    // feasibility (src/test/kkt.cpp:149-183), thread = constraint
+    bool ok = true;
+    {
+      const double * blb = p.bl + b * p.sbl;
+      const double * bub = p.bu + b * p.sbu;
+      for(int c = tid; c < mc; c += T)
+      {
+        const double cx = dot4_strided(n, Cb + (long long)c * p.ldc, 1, xs);
+        ok = ok && check_kkt_constraint(cx, blb[c], bub[c], us[c], tau_x, tau_u);
+      }
+      if(nb)
+      {
+        const double * xlb = p.xl + b * p.sxl;
+        const double * xub = p.xu + b * p.sxu;
+        for(int i = tid; i < nb; i += T) ok = ok && check_kkt_constraint(xs[i], xlb[i], xub[i], us[mc + i], tau_x, tau_u);
+      }
+    }
+    const int feas = __syncthreads_and(ok ? 1 : 0);
+
+    if(tid < 32)
+    {
+      int fl = (ndL <= tau_u ? 1 : 0) | (feas ? 2 : 0);
+      double d2 = 0.0;
+      if(p.x_ref)
+      {
+        // Eigen isApprox: |x - x*|^2 <= prec^2 min(|x|^2, |x*|^2), squared norms in the dot32 order
+        const double * xr = p.x_ref + b * n;
+        double sd = 0.0, s1 = 0.0, s2 = 0.0;
+        for(int k = tid; k < n; k += 32)
+        {
+          const double xv = xs[k], rv = xr[k], dv = xv - rv;
+          sd = fma(dv, dv, sd);
+          s1 = fma(xv, xv, s1);
+          s2 = fma(rv, rv, s2);
+        }
+        d2 = warp_sum32_kkt(sd);
+        const double n1 = warp_sum32_kkt(s1), n2 = warp_sum32_kkt(s2);
+        if(d2 <= (p.prec * p.prec) * fmin(n1, n2)) fl |= 4;
+      }
+      if(tid == 0)
+      {
+        p.flags[b] = fl;
+        if(p.resid)
+        {
+          double * r = p.resid + 4 * b;
+          r[0] = ndL;
+          r[1] = tau_u;
+          r[2] = tau_x;
+          r[3] = d2;
+        }
+        if(p.n_fail && fl != (p.x_ref ? 7 : 3)) atomicAdd(p.n_fail, 1ull);
+      }
+    }
+    __syncthreads(); // xs / us are rewritten by the next problem
+  }
+}
+
+template<int T>
+static cudaError_t launch_kkt(const KktParams & p, int num_sms, cudaStream_t st)
+{
+  const int smem = (int)sizeof(double) * (p.n + p.mc + p.nb + T / 32 + 2);
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kkt_check_kernel<T>, T, smem);
+  if(e != cudaSuccess) return e;
+  const long long grid = std::min<long long>(p.batch, (long long)std::max(occ, 1) * num_sms);
+  kkt_check_kernel<T><<<(unsigned)grid, T, smem, st>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+static int kkt_validate(const jrlqp_problem * pb, const jrlqp_kkt_args * k)
+{
+  if(!pb || !k || pb->batch < 0) return JRLQP_ERR_ARG;
+  if(k->n < 1 || k->n > 1024 || k->mc < 0 || k->mc > 8192) return JRLQP_ERR_ARG;
+  if(!pb->G || !pb->a || !k->x || !k->u || !k->flags || pb->ldg < k->n) return JRLQP_ERR_ARG;
+  if(k->mc > 0 && (!pb->C || !pb->bl || !pb->bu || pb->ldc < k->n)) return JRLQP_ERR_ARG;
+  if(k->use_bounds && (!pb->xl || !pb->xu)) return JRLQP_ERR_ARG;
+  return JRLQP_OK;
+}
+
+static int kkt_launch(const jrlqp_problem * pb, const jrlqp_kkt_args * k, int device, cudaStream_t st)
+{
+  cudaDeviceProp prop;
+  if(cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return JRLQP_ERR_CUDA;
+  if(cudaSetDevice(device) != cudaSuccess) return JRLQP_ERR_CUDA;
+  KktParams p{};
+  p.n = k->n;
+  p.mc = k->mc;
+  p.nb = k->use_bounds ? k->n : 0;
+  p.ldg = pb->ldg;
+  p.ldc = k->mc ? pb->ldc : k->n;
+  p.batch = pb->batch;
+  p.G = pb->G, p.sG = pb->G_stride;
+  p.a = pb->a, p.sa = pb->a_stride;
+  p.C = pb->C, p.sC = pb->C_stride;
+  p.bl = pb->bl, p.sbl = pb->bl_stride;
+  p.bu = pb->bu, p.sbu = pb->bu_stride;
+  p.xl = pb->xl, p.sxl = pb->xl_stride;
+  p.xu = pb->xu, p.sxu = pb->xu_stride;
+  p.x = k->x, p.u = k->u, p.x_ref = k->x_ref;
+  p.tau_p = k->tau_p, p.tau_d = k->tau_d, p.prec = k->prec;
+  p.flags = k->flags;
+  p.resid = k->resid;
+  p.n_fail = reinterpret_cast<unsigned long long *>(k->n_fail);
+  const int work = std::max(k->n, k->mc);
+  cudaError_t e;
+  if(work <= 64)
+    e = launch_kkt<64>(p, prop.multiProcessorCount, st);
+  else if(work <= 128)
+    e = launch_kkt<128>(p, prop.multiProcessorCount, st);
+  else
+    e = launch_kkt<256>(p, prop.multiProcessorCount, st);
+  return e == cudaSuccess ? JRLQP_OK : JRLQP_ERR_CUDA;
+}
+
+} // namespace jrlqp
+
+using namespace jrlqp;
+
+extern "C"
+{
+
+void jrlqp_kkt_default_args(jrlqp_kkt_args * k)
+{
+  if(!k) return;
+  *k = jrlqp_kkt_args{};
+  k->tau_p = 1e-6; // include/jrl-qp/test/kkt.h:83-84
+  k->tau_d = 1e-6;
+  k->prec = 1e-6; // tests/GoldfarbIdnaniSolverTest.cpp:94
+}
+
+int jrlqp_kkt_check_device(const jrlqp_problem * pb, const jrlqp_kkt_args * k, int32_t device, void * stream)
+{
+  int rc = kkt_validate(pb, k);
+  if(rc != JRLQP_OK) return rc;
+  if(pb->batch == 0) return JRLQP_OK;
+  return kkt_launch(pb, k, device, (cudaStream_t)stream);
+}
+
+int jrlqp_kkt_check_host(const jrlqp_problem * pb, const jrlqp_kkt_args * k, int32_t device)
+{
+  int rc = kkt_validate(pb, k);
+  if(rc != JRLQP_OK) return rc;
+  const long long B = pb->batch;
+  if(B == 0) return 0;
+  if(cudaSetDevice(device) != cudaSuccess) return JRLQP_ERR_CUDA;
+  const long long n = k->n, mc = k->mc, nb = k->use_bounds ? n : 0, m = mc + nb;
+  std::vector<void *> owned;
+  bool bad = false;
+  // dense device copy of `count` instances of a rows x cols column-major block (leading dimension ld)
+  auto up = [&](const double * h, long long stride, int rows, int cols, int ld, long long & dstride) -> const double *
+  {
+    if(!h || bad) return nullptr;
+    const long long blk = (long long)rows * cols;
+    const long long count = stride == 0 ? 1 : B;
+    double * d = nullptr;
+    if(cudaMalloc(&d, sizeof(double) * (size_t)(blk * count)) != cudaSuccess)
+    {
+      bad = true;
+      return nullptr;
+    }
+    owned.push_back(d);
+    cudaError_t e;
+    if(ld == rows && (stride == blk || count == 1))
+      e = cudaMemcpy(d, h, sizeof(double) * (size_t)(blk * count), cudaMemcpyHostToDevice);
+    else if(ld == rows)
+      e = cudaMemcpy2D(d, sizeof(double) * blk, h, sizeof(double) * stride, sizeof(double) * blk, (size_t)count, cudaMemcpyHostToDevice);
+    else
+    {
+      e = cudaSuccess;
+      for(long long q = 0; q < count && e == cudaSuccess; ++q)
+        e = cudaMemcpy2D(d + q * blk, sizeof(double) * rows, h + q * stride, sizeof(double) * ld, sizeof(double) * rows, (size_t)cols, cudaMemcpyHostToDevice);
+    }
+    if(e != cudaSuccess) bad = true;
+    dstride = stride == 0 ? 0 : blk;
+    return d;
+  };
+  jrlqp_problem dp{};
+  dp.batch = B;
+  long long s = 0;
+  dp.G = up(pb->G, pb->G_stride, (int)n, (int)n, pb->ldg, s), dp.G_stride = s, dp.ldg = (int)n;
+  dp.a = up(pb->a, pb->a_stride, (int)n, 1, (int)n, s), dp.a_stride = s;
+  dp.ldc = (int)n;
+  if(mc)
+  {
+    dp.C = up(pb->C, pb->C_stride, (int)n, (int)mc, pb->ldc, s), dp.C_stride = s;
+    dp.bl = up(pb->bl, pb->bl_stride, (int)mc, 1, (int)mc, s), dp.bl_stride = s;
+    dp.bu = up(pb->bu, pb->bu_stride, (int)mc, 1, (int)mc, s), dp.bu_stride = s;
+  }
+  if(nb)
+  {
+    dp.xl = up(pb->xl, pb->xl_stride, (int)n, 1, (int)n, s), dp.xl_stride = s;
+    dp.xu = up(pb->xu, pb->xu_stride, (int)n, 1, (int)n, s), dp.xu_stride = s;
+  }
+  jrlqp_kkt_args dk = *k;
+  dk.x = up(k->x, n, (int)n, 1, (int)n, s);
+  dk.u = up(k->u, std::max<long long>(m, 1), (int)std::max<long long>(m, 1), 1, (int)std::max<long long>(m, 1), s);
+  dk.x_ref = k->x_ref ? up(k->x_ref, n, (int)n, 1, (int)n, s) : nullptr;
+  int * d_flags = nullptr;
+  double * d_resid = nullptr;
+  unsigned long long * d_fail = nullptr;
+  if(!bad && cudaMalloc(&d_flags, sizeof(int) * (size_t)B) != cudaSuccess) bad = true;
+  if(d_flags) owned.push_back(d_flags);
+  if(!bad && k->resid && cudaMalloc(&d_resid, sizeof(double) * 4 * (size_t)B) != cudaSuccess) bad = true;
+  if(d_resid) owned.push_back(d_resid);
+  if(!bad && cudaMalloc(&d_fail, sizeof(unsigned long long)) != cudaSuccess) bad = true;
+  if(d_fail) owned.push_back(d_fail);
+  unsigned long long nfail = 0;
+  if(!bad)
+  {
+    bad = cudaMemset(d_fail, 0, sizeof(unsigned long long)) != cudaSuccess;
+    dk.flags = d_flags;
+    dk.resid = d_resid;
+    dk.n_fail = reinterpret_cast<int64_t *>(d_fail);
+    if(!bad) bad = kkt_launch(&dp, &dk, device, nullptr) != JRLQP_OK;
+    if(!bad) bad = cudaMemcpy(k->flags, d_flags, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if(!bad && k->resid) bad = cudaMemcpy(k->resid, d_resid, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if(!bad) bad = cudaMemcpy(&nfail, d_fail, sizeof(nfail), cudaMemcpyDeviceToHost) != cudaSuccess;
+    if(!bad && k->n_fail) *k->n_fail = (int64_t)nfail;
+  }
+  for(void * q : owned) cudaFree(q);
+  if(bad) return JRLQP_ERR_CUDA;
+  return (int)std::min<unsigned long long>(nfail, 0x7fffffffull);
+}
+
+} // extern "C"

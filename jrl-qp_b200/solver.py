@@ -93,6 +93,18 @@ class _Result(C.Structure):
                 ("n_active", C.c_void_p), ("L", C.c_void_p)]
 
 
+class _Sequence(C.Structure):
+    _fields_ = [("steps", C.c_int32), ("warm", C.c_int32), ("a_step_stride", C.c_int64), ("x_step_stride", C.c_int64),
+                ("u_step_stride", C.c_int64), ("f_step_stride", C.c_int64), ("iterations_step_stride", C.c_int64),
+                ("status_step_stride", C.c_int64), ("iterations_total", C.c_void_p), ("status_worst", C.c_void_p)]
+
+
+class _KktArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("mc", C.c_int32), ("use_bounds", C.c_int32), ("tau_p", C.c_double), ("tau_d", C.c_double),
+                ("prec", C.c_double), ("x", C.c_void_p), ("u", C.c_void_p), ("x_ref", C.c_void_p), ("flags", C.c_void_p),
+                ("resid", C.c_void_p), ("n_fail", C.c_void_p)]
+
+
 class KernelInfo(C.Structure):
     _fields_ = [("threads_per_qp", C.c_int32), ("rows_per_thread", C.c_int32), ("smem_bytes_per_qp", C.c_int32),
                 ("qps_per_sm", C.c_int32), ("grid", C.c_int32), ("num_sms", C.c_int32), ("stage_c", C.c_int32),
@@ -110,6 +122,8 @@ EXPORTED_SYMBOLS = [
     "jrlqp_structured_llt_device", "jrlqp_structured_llt_host", "jrlqp_structured_solve_device",
     "jrlqp_structured_solve_host", "jrlqp_structured_get_info", "jrlqp_selftest_arith",
     "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host", "jrlqp_set_kernel_path",
+    "jrlqp_solve_sequence_device", "jrlqp_solve_sequence_host",
+    "jrlqp_kkt_default_args", "jrlqp_kkt_check_device", "jrlqp_kkt_check_host",
 ]
 
 _lib = None
@@ -141,6 +155,12 @@ def load_library():
         lib.jrlqp_solve_batch_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
         lib.jrlqp_solve_batch_warm_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
         lib.jrlqp_solve_batch_warm_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
+        lib.jrlqp_solve_sequence_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Sequence), C.POINTER(_Result), C.c_void_p]
+        lib.jrlqp_solve_sequence_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Sequence), C.POINTER(_Result)]
+        lib.jrlqp_kkt_default_args.argtypes = [C.POINTER(_KktArgs)]
+        lib.jrlqp_kkt_default_args.restype = None
+        lib.jrlqp_kkt_check_device.argtypes = [C.POINTER(_Problem), C.POINTER(_KktArgs), C.c_int32, C.c_void_p]
+        lib.jrlqp_kkt_check_host.argtypes = [C.POINTER(_Problem), C.POINTER(_KktArgs), C.c_int32]
         lib.jrlqp_structured_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int32]
         lib.jrlqp_structured_destroy.argtypes = [C.c_void_p]
         lib.jrlqp_structured_last_error.restype = C.c_char_p
@@ -326,6 +346,113 @@ class BatchedGoldfarbIdnaniSolver:
             rc = self._lib.jrlqp_solve_batch_device(self._h, C.byref(pb), C.byref(res), C.c_void_p(stream))
         if rc != 0:
             raise JrlQpError(f"jrlqp_solve_batch_device failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
+
+
+    def solve_sequence(self, G, a_seq, Cm, bl, bu, xl=None, xu=None, warm=True, as_in=None, keep_steps=False):
+        """The reference's warm-start benchmark loop (benchmarks/SolversWarmStart.cpp:234-276) for a whole batch:
+        a_seq [T, B, n] are the linear terms of T consecutive steps, G / C / bounds as in solve(). warm=True: the
+        experimental solver, every step warm-started from the active set of the previous one (the first from
+        as_in, if given); warm=False: T cold solves of the stable solver. HOST arrays. Results in self.last:
+        the outputs of the last step (x, u, f, iterations, status [T, B, ...] when keep_steps), plus
+        iterations_total and status_worst [B]."""
+        f64 = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        G, a_seq, Cm, bl, bu, xl, xu = map(f64, (G, a_seq, Cm, bl, bu, xl, xu))
+        if self.nb == 0:
+            xl = xu = None
+        n, mc, m = self.n, self.mc, self.m
+        T, B = a_seq.shape[0], a_seq.shape[1]
+        full = {"G": 3, "C": 3, "bl": 2, "bu": 2, "xl": 2, "xu": 2}
+        arrs = {"G": G, "C": Cm, "bl": bl, "bu": bu, "xl": xl, "xu": xu}
+        shared = {k for k, v in arrs.items() if v is not None and v.ndim < full[k]}
+        if mc == 0:
+            Cm = bl = bu = None
+        lead = (T,) if keep_steps else ()
+        x = np.empty(lead + (B, n))
+        u = np.empty(lead + (B, m))
+        f = np.empty(lead + (B,))
+        it = np.empty(lead + (B,), dtype=np.int32)
+        status = np.empty(lead + (B,), dtype=np.int32)
+        act = np.empty((B, m), dtype=np.int8)
+        alist = np.empty((B, n), dtype=np.int32)
+        nact = np.empty(B, dtype=np.int32)
+        it_total = np.empty(B, dtype=np.int32)
+        worst = np.empty(B, dtype=np.int32)
+        pb = self._problem(B, G, a_seq, Cm, bl, bu, xl, xu, shared)
+        if as_in is not None:
+            as_in = np.ascontiguousarray(as_in, dtype=np.int8)
+            pb.as_in, pb.as_stride = _ptr(as_in), (m if as_in.ndim == 2 else 0)
+        k = 1 if keep_steps else 0
+        seq = _Sequence(T, int(bool(warm)), B * n, k * B * n, k * B * m, k * B, k * B, k * B, _ptr(it_total), _ptr(worst))
+        res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(it), _ptr(status), _ptr(act), _ptr(alist), _ptr(nact), None)
+        rc = self._lib.jrlqp_solve_sequence_host(self._h, C.byref(pb), C.byref(seq), C.byref(res))
+        if rc < 0:
+            raise JrlQpError(f"jrlqp_solve_sequence_host failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
+        self.last = dict(x=x, u=u, f=f, iterations=it, status=status, active_set=act, active_list=alist, n_active=nact,
+                         iterations_total=it_total, status_worst=worst, worst=rc)
+        return TerminationStatus(rc)
+
+    def solve_sequence_device(self, B, steps, G, a_seq, Cm, bl, bu, xl, xu, x, active_set, u=None, f=None, iterations=None,
+                              status=None, iterations_total=None, status_worst=None, warm=True, as_in=None, stream=0,
+                              shared=(), a_step_stride=None, step_strides=None):
+        """DEVICE pointers; asynchronous on `stream`. a_seq: [steps, B, n]; outputs of the last step unless
+        step_strides = {"x": ..., "u": ..., "f": ..., "iterations": ..., "status": ...} (elements) are given."""
+        pb = self._problem(B, G, a_seq, Cm, bl, bu, xl, xu, set(shared))
+        if as_in is not None:
+            pb.as_in, pb.as_stride = _ptr(as_in), self.m
+        ss = step_strides or {}
+        seq = _Sequence(int(steps), int(bool(warm)), int(a_step_stride if a_step_stride is not None else B * self.n),
+                        int(ss.get("x", 0)), int(ss.get("u", 0)), int(ss.get("f", 0)), int(ss.get("iterations", 0)),
+                        int(ss.get("status", 0)), _ptr(iterations_total), _ptr(status_worst))
+        res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(iterations), _ptr(status), _ptr(active_set), None, None, None)
+        rc = self._lib.jrlqp_solve_sequence_device(self._h, C.byref(pb), C.byref(seq), C.byref(res), C.c_void_p(stream))
+        if rc != 0:
+            raise JrlQpError(f"jrlqp_solve_sequence_device failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
+
+    def _kkt_args(self, x, u, x_ref, flags, resid, n_fail, tau_p, tau_d, prec):
+        k = _KktArgs()
+        self._lib.jrlqp_kkt_default_args(C.byref(k))
+        k.n, k.mc, k.use_bounds = self.n, self.mc, int(self.nb > 0)
+        if tau_p is not None:
+            k.tau_p = tau_p
+        if tau_d is not None:
+            k.tau_d = tau_d
+        if prec is not None:
+            k.prec = prec
+        k.x, k.u, k.x_ref, k.flags, k.resid, k.n_fail = _ptr(x), _ptr(u), _ptr(x_ref), _ptr(flags), _ptr(resid), _ptr(n_fail)
+        return k
+
+    def test_kkt(self, x, u, G, a, Cm, bl, bu, xl=None, xu=None, x_ref=None, tau_p=None, tau_d=None, prec=None):
+        """jrl::qp::test::testKKT (src/test/kkt.cpp:87-195) for a batch, on the GPU. HOST arrays laid out as in
+        solve(). Returns (flags [B] int32: bit 0 stationarity, bit 1 feasibility, bit 2 x ~ x_ref; resid [B, 4]:
+        |dL|_inf, tau_u, tau_x, |x - x_ref|^2; number of failing instances)."""
+        f64 = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        G, a, Cm, bl, bu, xl, xu, x, u, x_ref = map(f64, (G, a, Cm, bl, bu, xl, xu, x, u, x_ref))
+        if self.nb == 0:
+            xl = xu = None
+        if self.mc == 0:
+            Cm = bl = bu = None
+        full = {"G": 3, "a": 2, "C": 3, "bl": 2, "bu": 2, "xl": 2, "xu": 2}
+        arrs = {"G": G, "a": a, "C": Cm, "bl": bl, "bu": bu, "xl": xl, "xu": xu}
+        shared = {k for k, v in arrs.items() if v is not None and v.ndim < full[k]}
+        B = x.shape[0]
+        flags = np.empty(B, dtype=np.int32)
+        resid = np.empty((B, 4))
+        n_fail = np.zeros(1, dtype=np.int64)
+        pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, shared)
+        k = self._kkt_args(x, u, x_ref, flags, resid, n_fail, tau_p, tau_d, prec)
+        rc = self._lib.jrlqp_kkt_check_host(C.byref(pb), C.byref(k), self.device)
+        if rc < 0:
+            raise JrlQpError(f"jrlqp_kkt_check_host failed ({rc})")
+        return flags, resid, int(n_fail[0])
+
+    def test_kkt_device(self, B, x, u, G, a, Cm, bl, bu, xl, xu, flags, resid=None, n_fail=None, x_ref=None, shared=(),
+                        tau_p=None, tau_d=None, prec=None, stream=0):
+        """Same check on DEVICE pointers, asynchronous on `stream` (n_fail: zeroed device int64 counter)."""
+        pb = self._problem(B, G, a, Cm, bl, bu, xl, xu, set(shared))
+        k = self._kkt_args(x, u, x_ref, flags, resid, n_fail, tau_p, tau_d, prec)
+        rc = self._lib.jrlqp_kkt_check_device(C.byref(pb), C.byref(k), self.device, C.c_void_p(stream))
+        if rc != 0:
+            raise JrlQpError(f"jrlqp_kkt_check_device failed ({rc})")
 
 
 class GoldfarbIdnaniSolver:

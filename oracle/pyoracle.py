@@ -239,3 +239,28 @@ def decomp_solve(st, data, M, transpose=False, start=0, end=-1, nthreads=1):
     lib().decomp_oracle_solve(*args, _dp(data), C.c_long(stride), _dp(M), C.c_int(n), C.c_int(ncols), C.c_long(ncols * n),
                               C.c_long(B), C.c_int(1 if transpose else 0), C.c_int(start), C.c_int(end), C.c_int(nthreads))
     return M
+
+
+def kkt_check_batch(x, u, G, a, Cm, bl, bu, xl=None, xu=None, x_ref=None, tau_p=1e-6, tau_d=1e-6, prec=1e-6, nthreads=1):
+    """Restatement of jrl::qp::test::testKKT (src/test/kkt.cpp) for a batch, arrays laid out as in solve_batch.
+    Returns (flags [B] int32, resid [B,4], n_fail)."""
+    G, a, Cm, bl, bu, xl, xu, x, u, x_ref = map(_f64, (G, a, Cm, bl, bu, xl, xu, x, u, x_ref))
+    n = G.shape[-1]
+    mc = Cm.shape[-2] if (Cm is not None and Cm.size) else 0
+    nb = n if xl is not None and xl.size else 0
+    B = x.shape[0]
+    flags = np.empty(B, dtype=np.int32)
+    resid = np.empty((B, 4))
+    if mc == 0:
+        Cm = bl = bu = np.zeros((1,))
+    nf = lib().kkt_oracle_check_batch(
+        C.c_int(n), C.c_int(mc), C.c_int(nb), C.c_long(B),
+        _dp(G), C.c_long(n * n if G.ndim == 3 else 0), C.c_int(n),
+        _dp(a), C.c_long(n if a.ndim == 2 else 0),
+        _dp(Cm), C.c_long(mc * n if Cm.ndim == 3 else 0), C.c_int(n),
+        _dp(bl), C.c_long(mc if bl.ndim == 2 else 0), _dp(bu), C.c_long(mc if bu.ndim == 2 else 0),
+        _dp(xl), C.c_long(n if (xl is not None and xl.ndim == 2) else 0),
+        _dp(xu), C.c_long(n if (xu is not None and xu.ndim == 2) else 0),
+        _dp(x), _dp(u), _dp(x_ref), C.c_double(tau_p), C.c_double(tau_d), C.c_double(prec),
+        _ip(flags), _dp(resid), C.c_int(nthreads))
+    return flags, resid, int(nf)

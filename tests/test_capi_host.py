@@ -39,6 +39,8 @@ def test_struct_mirrors_match_header_sizes():
     assert C.sizeof(S._Problem) == 8 * 19
     assert C.sizeof(S._Result) == 8 * 9
     assert C.sizeof(S.KernelInfo) == 4 * 8
+    assert C.sizeof(S._Sequence) == 72  # 2 x int32, 6 x int64, 2 pointers
+    assert C.sizeof(S._KktArgs) == 88  # 3 x int32 (+4 pad), 3 doubles, 6 pointers
 
 
 def test_default_options_match_reference():
