@@ -17,8 +17,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["gi_oracle.cpp", "gi_oracle_capi.cpp", "decomp_oracle.cpp", "decomp_oracle_capi.cpp", "warm_oracle.cpp", "warm_oracle_capi.cpp", "kkt_oracle.cpp"]
-HEADERS = ["gi_oracle.hpp", "decomp_oracle.hpp", "warm_oracle.hpp"]
+SOURCES = ["gi_oracle.cpp", "gi_oracle_capi.cpp", "decomp_oracle.cpp", "decomp_oracle_capi.cpp", "warm_oracle.cpp", "warm_oracle_capi.cpp", "kkt_oracle.cpp", "block_oracle.cpp"]
+HEADERS = ["gi_oracle.hpp", "decomp_oracle.hpp", "warm_oracle.hpp", "block_oracle.hpp"]
 BASE_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-pthread", "-DNDEBUG", "-Wall", "-Wextra"]
 VARIANTS = {"fma": ["-mfma", "-mavx2"], "generic": []}
 

@@ -241,6 +241,96 @@ def decomp_solve(st, data, M, transpose=False, start=0, end=-1, nthreads=1):
     return M
 
 
+class CStructure:
+    """Block-diagonal constraint matrix (structured::StructuredC, src/structured/StructuredC.cpp:9-25): block i is
+    nvar[i] x ncstr[i], column-major (one constraint normal per column) at element offset `offset[i]` from the instance
+    base, leading dimension ld[i]. `stride` = elements per instance."""
+
+    def __init__(self, nvar, ncstr, offset, ld, stride):
+        self.nvar = np.asarray(nvar, dtype=np.int32)
+        self.ncstr = np.asarray(ncstr, dtype=np.int32)
+        self.offset = np.asarray(offset, dtype=np.int64)
+        self.ld = np.asarray(ld, dtype=np.int32)
+        self.stride = int(stride)
+        self.n = int(self.nvar.sum())
+        self.mc = int(self.ncstr.sum())
+
+    @classmethod
+    def packed(cls, nvar, ncstr):
+        nvar = np.asarray(nvar, dtype=np.int64)
+        ncstr = np.asarray(ncstr, dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(nvar * ncstr)])
+        return cls(nvar, ncstr, off[:-1], nvar, int(off[-1]))
+
+    @classmethod
+    def dense(cls, nvar, ncstr, ld=None):
+        """Blocks are views into a dense column-major n x mc matrix (tests/BlockGISolverTest.in.cpp:90-100)."""
+        nvar = np.asarray(nvar, dtype=np.int64)
+        ncstr = np.asarray(ncstr, dtype=np.int64)
+        n, mc = int(nvar.sum()), int(ncstr.sum())
+        ld = n if ld is None else int(ld)
+        r0 = np.concatenate([[0], np.cumsum(nvar)])[:-1]
+        c0 = np.concatenate([[0], np.cumsum(ncstr)])[:-1]
+        return cls(nvar, ncstr, r0 + c0 * ld, np.full(len(nvar), ld), ld * mc)
+
+    def pack(self, Cd):
+        """Dense [B, mc, n] (row j = normal of constraint j) -> data [B, stride] in this layout."""
+        Cd = np.asarray(Cd, dtype=np.float64)
+        B = Cd.shape[0]
+        data = np.zeros((B, self.stride))
+        r0 = np.concatenate([[0], np.cumsum(self.nvar)])
+        c0 = np.concatenate([[0], np.cumsum(self.ncstr)])
+        for i in range(len(self.nvar)):
+            for j in range(int(self.ncstr[i])):
+                o = int(self.offset[i]) + j * int(self.ld[i])
+                data[:, o:o + int(self.nvar[i])] = Cd[:, c0[i] + j, r0[i]:r0[i + 1]]
+        return data
+
+    def to_dense(self, data):
+        """data [B, stride] -> dense [B, mc, n]."""
+        B = data.shape[0]
+        out = np.zeros((B, self.mc, self.n))
+        r0 = np.concatenate([[0], np.cumsum(self.nvar)])
+        c0 = np.concatenate([[0], np.cumsum(self.ncstr)])
+        for i in range(len(self.nvar)):
+            for j in range(int(self.ncstr[i])):
+                o = int(self.offset[i]) + j * int(self.ld[i])
+                out[:, c0[i] + j, r0[i]:r0[i + 1]] = data[:, o:o + int(self.nvar[i])]
+        return out
+
+
+def block_solve_batch(stG, stC, Gdata, a, Cdata, bl, bu, xl=None, xu=None, max_iter=500, big_bnd=1e100, nthreads=1, want_L=False):
+    """Restatement of experimental::BlockGISolver::solve, batched. stG: structure of G (type, sizes, diag_offset, diag_ld,
+    off_offset, off_ld, stride), Gdata [B, stride] or [stride] (shared; never modified: the oracle factorises a private copy),
+    stC: CStructure, Cdata [B, stride] or [stride], a [B, n] or [n], bl/bu [B, mc] or [mc], xl/xu [B, n], [n] or None."""
+    Gdata, a, Cdata, bl, bu, xl, xu = map(_f64, (Gdata, a, Cdata, bl, bu, xl, xu))
+    n, mc = stC.n, stC.mc
+    assert n == int(np.sum(stG.sizes))
+    nb = n if xl is not None else 0
+    m = mc + nb
+    B = max(arr.shape[0] if arr.ndim == 2 else 1 for arr in (Gdata, a, Cdata, bl, bu))
+    out = dict(x=np.zeros((B, n)), u=np.zeros((B, m)), f=np.zeros(B), iterations=np.zeros(B, dtype=np.int32),
+               status=np.zeros(B, dtype=np.int32), active_set=np.zeros((B, m), dtype=np.int8),
+               active_list=np.zeros((B, n), dtype=np.int32), n_active=np.zeros(B, dtype=np.int32),
+               q_doubles=np.zeros(B, dtype=np.int64))
+    L = np.zeros((B, stG.stride)) if want_L else None
+    args, keep = _desc_args(stG)
+    cn, cm = np.ascontiguousarray(stC.nvar, dtype=np.int32), np.ascontiguousarray(stC.ncstr, dtype=np.int32)
+    co, cl = np.ascontiguousarray(stC.offset, dtype=np.int64), np.ascontiguousarray(stC.ld, dtype=np.int32)
+    st = lambda arr, per: 0 if arr is None or arr.ndim == 1 else per  # noqa: E731
+    worst = lib().block_oracle_solve_batch(
+        *args, C.c_long(stG.stride), C.c_int(len(cn)), _ip(cn), _ip(cm), co.ctypes.data_as(c_lp), _ip(cl), C.c_int(1 if nb else 0),
+        C.c_long(B), _dp(Gdata), C.c_long(st(Gdata, stG.stride)), _dp(a), C.c_long(st(a, n)), _dp(Cdata), C.c_long(st(Cdata, stC.stride)),
+        _dp(bl), C.c_long(st(bl, mc)), _dp(bu), C.c_long(st(bu, mc)), _dp(xl), C.c_long(st(xl, n)), _dp(xu), C.c_long(st(xu, n)),
+        C.c_int(max_iter), C.c_double(big_bnd), _dp(out["x"]), _dp(out["u"]), _dp(out["f"]), _ip(out["iterations"]), _ip(out["status"]),
+        out["active_set"].ctypes.data_as(c_bp), _ip(out["active_list"]), _ip(out["n_active"]), _dp(L),
+        out["q_doubles"].ctypes.data_as(c_lp), C.c_int(nthreads))
+    out["worst"] = worst
+    if want_L:
+        out["L"] = L
+    return out
+
+
 def kkt_check_batch(x, u, G, a, Cm, bl, bu, xl=None, xu=None, x_ref=None, tau_p=1e-6, tau_d=1e-6, prec=1e-6, nthreads=1):
     """Restatement of jrl::qp::test::testKKT (src/test/kkt.cpp) for a batch, arrays laid out as in solve_batch.
     Returns (flags [B] int32, resid [B,4], n_fail)."""
