@@ -379,6 +379,86 @@ typedef struct jrlqp_structured_info
 } jrlqp_structured_info;
 int jrlqp_structured_get_info(const jrlqp_structured * s, jrlqp_structured_info * info);
 
+/* ---------------------------------------------------------------------------------------------
+ * Structured solver: experimental::BlockGISolver, batched.
+ *
+ * Replaces experimental::BlockGISolver::solve(StructuredG, a, StructuredC, bl, bu, xl, xu, as)
+ * (include/jrl-qp/experimental/BlockGISolver.h:24-46, src/experimental/BlockGISolver.cpp:18-60) and what it
+ * runs on: structured::StructuredJ (src/structured/StructuredJ.cpp:33-57), structured::StructuredQR
+ * (src/structured/StructuredQR.cpp:66-103), structured::StructuredC (src/structured/StructuredC.cpp:9-77),
+ * internal::OrthonormalSequence (src/internal/OrthonormalSequence.cpp:50-196) and the DualSolver loop
+ * (src/DualSolver.cpp:91-168): the dual active-set method with J = L^-T Q kept implicit — L the structured
+ * factor of G, Q a sequence of Householder reflectors (activations) and Givens sequences (drops).
+ * As in the reference, the solver handles cold starts of problems WITHOUT equalities: the reference asserts
+ * that no constraint is active after the initial scan (BlockGISolver.cpp:474); an instance whose data contain
+ * bl == bu or xl == xu is reported as JRLQP_INCONSISTENT_INPUT. Instances that exhaust the storage of the
+ * orthonormal sequence (2 n max_iter doubles per resident CTA) report JRLQP_UNKNOWN.
+ * --------------------------------------------------------------------------------------------- */
+
+/* structured::StructuredC(std::vector<MatrixConstRef>) (src/structured/StructuredC.cpp:9-25): block-diagonal
+ * constraint matrix. Block i is nvar[i] x ncstr[i], column-major (one constraint normal per column), at
+ * `offset[i]` elements from the instance base, leading dimension ld[i]. HOST arrays, copied at create. The
+ * nvar[i] must add up to the size of G; constraints are numbered block after block. */
+typedef struct jrlqp_cstructure
+{
+  int32_t nblocks;
+  const int32_t * nvar;
+  const int32_t * ncstr;
+  const int64_t * offset;
+  const int32_t * ld;
+} jrlqp_cstructure;
+
+/* One batch of structured problems; strides in ELEMENTS between instances, 0 = shared.
+ *   G  the blocks described by the jrlqp_structure given at create. With G_stride != 0 the blocks are
+ *      factorised IN PLACE, as the reference's pb_.G.lltInPlace() does on the caller's views
+ *      (BlockGISolver.cpp:71); a shared G (stride 0) is left untouched (one private copy is factorised).
+ *      The *_host entry point never writes to the caller's G.
+ *   C  the blocks described by the jrlqp_cstructure. */
+typedef struct jrlqp_block_problem
+{
+  int64_t batch;
+  double * G;
+  int64_t G_stride;
+  const double * a;
+  int64_t a_stride;
+  const double * C;
+  int64_t C_stride;
+  const double * bl;
+  int64_t bl_stride;
+  const double * bu;
+  int64_t bu_stride;
+  const double * xl; /* NULL <=> created without bounds */
+  int64_t xl_stride;
+  const double * xu;
+  int64_t xu_stride;
+} jrlqp_block_problem;
+
+typedef struct jrlqp_blockgi jrlqp_blockgi;
+
+/* BlockGISolver(nbVar, nbCstr, useBounds) (src/experimental/BlockGISolver.cpp:12-15) for one block structure. */
+int jrlqp_blockgi_create(jrlqp_blockgi ** out, const jrlqp_structure * G, const jrlqp_cstructure * C, int32_t use_bounds,
+                         int64_t batch_capacity, int32_t device);
+int jrlqp_blockgi_destroy(jrlqp_blockgi * s);
+const char * jrlqp_blockgi_last_error(const jrlqp_blockgi * s);
+/* DualSolver::options (max_iter, big_bnd; warm_start must be 0: see above) */
+int jrlqp_blockgi_set_options(jrlqp_blockgi * s, const jrlqp_options * opt);
+int jrlqp_blockgi_get_options(const jrlqp_blockgi * s, jrlqp_options * opt);
+/* solve() + the DualSolver accessors for the batch; jrlqp_result as for the dense solver (result.L is ignored:
+ * the factor is left in G). DEVICE pointers, asynchronous on `stream`. */
+int jrlqp_blockgi_solve_device(jrlqp_blockgi * s, const jrlqp_block_problem * pb, const jrlqp_result * res, void * stream);
+/* Same with HOST pointers; returns the worst jrlqp_termination_status (>= 0) or a negative JRLQP_ERR_*. */
+int jrlqp_blockgi_solve_host(jrlqp_blockgi * s, const jrlqp_block_problem * pb, const jrlqp_result * res);
+
+typedef struct jrlqp_blockgi_info
+{
+  int32_t n, mc, nb;
+  int32_t threads; /* per QP (one QP per CTA) */
+  int32_t smem_bytes, ctas_per_sm, grid, num_sms;
+  int64_t workspace_bytes_per_cta; /* packed R + storage of the orthonormal sequence */
+  int64_t g_elements_per_instance;
+} jrlqp_blockgi_info;
+int jrlqp_blockgi_get_info(const jrlqp_blockgi * s, jrlqp_blockgi_info * info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,22 +37,56 @@ def _listdir(d, exts):
     return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(exts))
 
 
+def _includes(path, seen=None):
+    """Transitive closure of the local #include "..." files of a source (for per-object staleness)."""
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as fh:
+        for line in fh:
+            line = line.strip()
+            if line.startswith("#include \""):
+                name = line.split("\"")[1]
+                for d in (os.path.dirname(path), CSRC, INCLUDE):
+                    cand = os.path.join(d, name)
+                    if os.path.exists(cand):
+                        _includes(cand, seen)
+                        break
+    return seen
+
+
 def build_cuda(force=False, verbose=False):
+    """One object per .cu (recompiled only when it or a header it includes changed), then one link."""
     os.makedirs(OUT, exist_ok=True)
     target = os.path.join(OUT, "libjrlqp_b200.so")
     srcs = _listdir(CSRC, (".cu",))
-    deps = srcs + _listdir(CSRC, (".cuh", ".h")) + _listdir(INCLUDE, (".h",))
-    if force or _newer(target, deps):
-        cmd = [NVCC] + NVCC_FLAGS + srcs + ["-o", target]
+    objs = []
+    logs = []
+    relink = force or not os.path.exists(target)
+    for src in srcs:
+        obj = os.path.join(OUT, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, sorted(_includes(src))):
+            cmd = [NVCC] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            logs.append(res.stdout + res.stderr)
+            with open(os.path.join(OUT, os.path.basename(src)[:-3] + ".ptxas.log"), "w") as fh:
+                fh.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed on " + src)
+            relink = True
+    if relink or _newer(target, objs):
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + objs + ["-o", target]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         res = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(OUT, "nvcc_ptxas.log")
-        with open(log, "w") as fh:
-            fh.write(res.stdout + res.stderr)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
-            raise RuntimeError("nvcc failed")
+            raise RuntimeError("nvcc link failed")
     return target
 
 

@@ -1,0 +1,765 @@
+// Structured dual active-set solver, batched: ONE QP PER CTA, persistent CTAs pulling problems from a
+// ticket counter.
+//
+// Replaces, for a batch of QPs sharing one block structure, experimental::BlockGISolver::solve
+// (src/experimental/BlockGISolver.cpp:18-60) and what it runs on:
+//   DualSolver::solve                         src/DualSolver.cpp:91-168 (the loop), :231-244 (add / remove)
+//   BlockGISolver::init_ and its helpers       src/experimental/BlockGISolver.cpp:62-109, 293-377, 454-484
+//   selectViolatedConstraint_ / computeStep_ / computeStepLength_ / dot_   :111-275
+//   structured::StructuredJ::premultByJt / premultByJ2   src/structured/StructuredJ.cpp:33-57
+//   structured::StructuredQR::RSolve / add / remove      src/structured/StructuredQR.cpp:66-103
+//   structured::StructuredC::col / transposeMult         src/structured/StructuredC.cpp:57-77
+//   internal::OrthonormalSequence (Householder / Givens elements, both directions)
+//                                                        src/internal/OrthonormalSequence.cpp:50-124,178-196
+// The matrix J = L^-T Q of the dense solver is never formed: L is the structured Cholesky factor of G
+// (structured.cuh, factorised by structured_llt_kernel before this kernel runs), Q the product of one
+// Householder reflector per activated constraint and one Givens sequence per dropped one, kept as a
+// growing list of records in a per-CTA slice of global memory (it stays in L2 for the sizes of the
+// reference's use cases). One iteration costs O(n nb) for the two structured solves plus O(sum of record
+// lengths) for the two passes over Q, instead of the O(n^2) of the dense solver.
+//
+// Mapping: vectors (x, z, d, u, r, one work vector), the active set and the record table live in shared
+// memory; the structured solves use every thread of the CTA (tile by tile, structured.cuh); the passes
+// over Q are one serial chain of short reflections (dot, scale, axpy over <= n elements), which ONE warp
+// runs with shuffle reductions and no block barrier; constraint scan and ratio test are block-wide
+// first-minimum reductions. Arithmetic: the canonical orders of oracle/block_oracle.hpp, so results are
+// bit-identical to the CPU oracle.
+#pragma once
+
+#include "structured.cuh"
+
+namespace jrlqp
+{
+
+struct BlockGiParams
+{
+  StructParams G; // descriptor; data = the factorised blocks (instance k at data + k * stride; stride 0: shared)
+  const int * llt_ok; // [batch] (or [1] when G is shared): 0 = not positive definite
+  int ok_stride;
+  // structured::StructuredC
+  int cb;
+  const int * cnvar; // [cb]
+  const long long * coff; // [cb]
+  const int * cld; // [cb]
+  const int * cvar0; // [cb + 1] first variable of block i
+  const int * ccstr0; // [cb + 1] first constraint of block i
+  const int * toblock; // [mc]
+  int mc, nb, max_iter;
+  double big_bnd;
+  const double *a, *C, *bl, *bu, *xl, *xu;
+  long long sa, sC, sbl, sbu, sxl, sxu;
+  double *x, *u, *f;
+  int *iters, *status;
+  signed char * act;
+  int *alist, *nact;
+  long long * qdoubles; // nullable: doubles of Q storage used (statistic)
+  double * ws; // per-CTA workspace: R packed (n (n + 1) / 2), then the Q records (qcap)
+  long long ws_stride, qcap;
+  long long batch;
+  unsigned long long * ticket;
+};
+
+enum : int
+{
+  BG_INACTIVE = 0,
+  BG_LOWER = 1,
+  BG_UPPER = 2,
+  BG_EQUALITY = 3,
+  BG_LOWER_BOUND = 4,
+  BG_UPPER_BOUND = 5,
+  BG_FIXED = 6
+};
+
+#define BG_FULL 0xffffffffu
+
+// Eigen JacobiRotation::makeGivens, real case (as gi_oracle.cpp makeGivens)
+__device__ __forceinline__ void bg_make_givens(double p, double q, double & c, double & s, double & r)
+{
+  if(q == 0.0)
+  {
+    c = p < 0.0 ? -1.0 : 1.0;
+    s = 0.0;
+    r = fabs(p);
+  }
+  else if(p == 0.0)
+  {
+    c = 0.0;
+    s = q < 0.0 ? 1.0 : -1.0;
+    r = fabs(q);
+  }
+  else if(fabs(p) > fabs(q))
+  {
+    const double t = q / p;
+    double u = sqrt(fma(t, t, 1.0));
+    if(p < 0.0) u = -u;
+    c = 1.0 / u;
+    s = -t * c;
+    r = p * u;
+  }
+  else
+  {
+    const double t = p / q;
+    double u = sqrt(fma(t, t, 1.0));
+    if(q < 0.0) u = -u;
+    s = -1.0 / u;
+    c = -t * s;
+    r = q * u;
+  }
+}
+
+struct BlockGi
+{
+  const BlockGiParams & P;
+  const int n, mc, m, T, tid, lane, warp, W;
+  const bool up;
+  // shared memory
+  double *x, *z, *d, *w, *u, *r, *scr, *Lt, *Bt;
+  int *rec, *alist, *iscr;
+  signed char * st;
+  // per problem
+  const double *base, *a, *C, *bl, *bu, *xl, *xu;
+  double *Rg, *Qg;
+  int q, nrec;
+  long long qoff;
+  double f;
+
+  __device__ BlockGi(const BlockGiParams & p, double * sm)
+  : P(p), n(p.G.n), mc(p.mc), m(p.mc + p.nb), T(blockDim.x), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5),
+    W(blockDim.x >> 5), up(p.G.type == SG_ARROW_UP)
+  {
+    const int ne = (n + 2) & ~1;
+    x = sm;
+    z = x + ne;
+    d = z + ne;
+    w = d + ne;
+    u = w + ne;
+    r = u + ne;
+    scr = r + ne;
+    Lt = scr + 80;
+    Bt = Lt + p.G.nmax * p.G.nmax;
+    rec = reinterpret_cast<int *>(Bt + p.G.nmax * p.G.nmax);
+    alist = rec + 3 * p.max_iter;
+    iscr = alist + n;
+    st = reinterpret_cast<signed char *>(iscr + 16);
+    double * slot = p.ws + (long long)blockIdx.x * p.ws_stride;
+    Rg = slot;
+    Qg = slot + (long long)n * (n + 1) / 2;
+  }
+
+  static __host__ __device__ long long smem_bytes(int n, int nmax, int m, int max_iter)
+  {
+    const long long ne = (n + 2) & ~1;
+    return (6 * ne + 80 + 2LL * nmax * nmax) * 8 + (3LL * max_iter + n + 16) * 4 + ((m + 15) & ~15);
+  }
+
+  __device__ __forceinline__ int pidx(int i) const { return up ? sg_perm(P.G, i) : i; }
+  __device__ __forceinline__ static long long colR(int k) { return (long long)k * (k + 1) / 2; }
+
+  // C.col(p).dot(v) (StructuredC::col + SingleNZSegmentVector::dot): dot4 over the rows of the block
+  __device__ __forceinline__ double col_dot(int p, const double * v) const
+  {
+    const int bi = P.toblock[p];
+    const double * c = C + P.coff[bi] + (long long)(p - P.ccstr0[bi]) * P.cld[bi];
+    return dot4_rows(P.cnvar[bi], c, 1, v + P.cvar0[bi], 1);
+  }
+
+  // dot32(len, a, b) by warp 0, result to every thread. a, b: global or shared.
+  __device__ __forceinline__ double block_dot32(int len, const double * pa, const double * pb)
+  {
+    __syncthreads();
+    if(warp == 0)
+    {
+      double acc = 0;
+      for(int k = lane; k < len; k += 32) acc = fma(pa[k], pb[k], acc);
+      for(int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(BG_FULL, acc, off);
+      if(lane == 0) scr[0] = acc;
+    }
+    __syncthreads();
+    return scr[0];
+  }
+
+  // lexicographic minimum of (val, idx) over the CTA; threads without a candidate pass idx = INT_MAX
+  __device__ __forceinline__ void block_first_min(double & val, int & idx)
+  {
+    for(int off = 16; off >= 1; off >>= 1)
+    {
+      const double ov = __shfl_xor_sync(BG_FULL, val, off);
+      const int oi = __shfl_xor_sync(BG_FULL, idx, off);
+      if(oi != 0x7fffffff && (idx == 0x7fffffff || ov < val || (ov == val && oi < idx)))
+      {
+        val = ov;
+        idx = oi;
+      }
+    }
+    if(W > 1)
+    {
+      __syncthreads();
+      if(lane == 0)
+      {
+        scr[8 + warp] = val;
+        iscr[warp] = idx;
+      }
+      __syncthreads();
+      val = scr[8];
+      idx = iscr[0];
+      for(int k = 1; k < W; ++k)
+      {
+        const double ov = scr[8 + k];
+        const int oi = iscr[k];
+        if(oi != 0x7fffffff && (idx == 0x7fffffff || ov < val || (ov == val && oi < idx)))
+        {
+          val = ov;
+          idx = oi;
+        }
+      }
+    }
+  }
+
+  // ---- OrthonormalSequence::applyTransposeToTheLeft / applyToTheLeft on a vector in shared memory: warp 0 only
+  __device__ __forceinline__ void householder(const double * p, int len, double * v)
+  {
+    const double tau = p[0];
+    double acc = 0;
+    for(int k = lane; k < len; k += 32) acc = fma(k == 0 ? 1.0 : p[k], v[k], acc);
+    for(int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(BG_FULL, acc, off);
+    const double hd = tau * acc;
+    for(int k = lane; k < len; k += 32) v[k] = fma(-hd, k == 0 ? 1.0 : p[k], v[k]);
+    __syncwarp();
+  }
+
+  __device__ void apply_qt(double * v)
+  {
+    if(warp == 0)
+    {
+      for(int e = 0; e < nrec; ++e)
+      {
+        const int start = rec[3 * e], size = rec[3 * e + 1];
+        const double * p = Qg + rec[3 * e + 2];
+        double * vs = v + (start & 0x7fffffff);
+        if(start >= 0)
+          householder(p, size, vs);
+        else
+        {
+          // Givens(c, s)^T, i ascending: x' = c x - s y, y' = s x + c y; the y' of one rotation is the x of the next
+          double carry = vs[0];
+          for(int i0 = 0; i0 < size; i0 += 32)
+          {
+            const int k = min(i0 + lane, size - 1);
+            const double cl = p[k], sl = p[size + k];
+            const int cnt = min(32, size - i0);
+            for(int j = 0; j < cnt; ++j)
+            {
+              const double c = __shfl_sync(BG_FULL, cl, j), s = __shfl_sync(BG_FULL, sl, j);
+              const double xi = carry, yi = vs[i0 + j + 1];
+              const double nx = fma(c, xi, -(s * yi));
+              carry = fma(c, yi, s * xi);
+              if(lane == 0) vs[i0 + j] = nx;
+            }
+          }
+          if(lane == 0) vs[size] = carry;
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  __device__ void apply_q(double * v)
+  {
+    if(warp == 0)
+    {
+      for(int e = nrec - 1; e >= 0; --e)
+      {
+        const int start = rec[3 * e], size = rec[3 * e + 1];
+        const double * p = Qg + rec[3 * e + 2];
+        double * vs = v + (start & 0x7fffffff);
+        if(start >= 0)
+          householder(p, size, vs);
+        else
+        {
+          // Givens(c, s), i descending: x' = c x + s y, y' = -s x + c y; the x' of one rotation is the y of the next
+          double carry = vs[size];
+          for(int i1 = size; i1 > 0; i1 -= 32)
+          {
+            const int cnt = min(32, i1);
+            const int k = max(i1 - 1 - lane, 0);
+            const double cl = p[k], sl = p[size + k];
+            for(int j = 0; j < cnt; ++j)
+            {
+              const int i = i1 - 1 - j;
+              const double c = __shfl_sync(BG_FULL, cl, j), s = __shfl_sync(BG_FULL, sl, j);
+              const double xi = vs[i], yi = carry;
+              carry = fma(c, xi, s * yi);
+              const double ny = fma(c, yi, -(s * xi));
+              if(lane == 0) vs[i + 1] = ny;
+            }
+          }
+          if(lane == 0) vs[0] = carry;
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- selectViolatedConstraint_ (src/experimental/BlockGISolver.cpp:111-164)
+  __device__ __forceinline__ void slacks(int i, double & sl, double & su) const
+  {
+    if(i < mc)
+    {
+      const double cx = col_dot(i, x);
+      sl = cx - bl[i];
+      su = bu[i] - cx;
+    }
+    else
+    {
+      const int j = i - mc;
+      sl = x[j] - xl[j];
+      su = xu[j] - x[j];
+    }
+  }
+
+  // returns the constraint index (-1: none) and its status
+  __device__ int select(int & status)
+  {
+    double best = 0.0;
+    int code = 0x7fffffff;
+    bool both = false;
+    for(int i = tid; i < m; i += T)
+    {
+      if(st[i] != BG_INACTIVE) continue;
+      double sl, su;
+      slacks(i, sl, su);
+      const bool nl = sl < 0.0, nu = su < 0.0;
+      both |= nl && nu;
+      const double v = nl ? sl : su;
+      const int ci = 2 * i + (nl ? 0 : 1);
+      if((nl || nu) && (code == 0x7fffffff || v < best)) // i ascending inside a thread: strict < keeps the first
+      {
+        best = v;
+        code = ci;
+      }
+    }
+    if(__syncthreads_or(both))
+    {
+      // bl > bu somewhere: the `else if` chain of the reference is order dependent, replay it literally
+      if(tid == 0)
+      {
+        double smin = 0;
+        int c = 0x7fffffff;
+        for(int i = 0; i < m; ++i)
+        {
+          if(st[i] != BG_INACTIVE) continue;
+          double sl, su;
+          slacks(i, sl, su);
+          if(sl < smin)
+          {
+            smin = sl;
+            c = 2 * i;
+          }
+          else if(su < smin)
+          {
+            smin = su;
+            c = 2 * i + 1;
+          }
+        }
+        iscr[8] = c;
+      }
+      __syncthreads();
+      code = iscr[8];
+      __syncthreads();
+    }
+    else
+      block_first_min(best, code);
+    if(code == 0x7fffffff)
+    {
+      status = BG_INACTIVE;
+      return -1;
+    }
+    const int p = code >> 1;
+    status = p < mc ? ((code & 1) ? BG_UPPER : BG_LOWER) : ((code & 1) ? BG_UPPER_BOUND : BG_LOWER_BOUND);
+    return p;
+  }
+
+  // ---- computeStep_ (src/experimental/BlockGISolver.cpp:166-174)
+  __device__ void compute_step(int p, int status)
+  {
+    // d = Q^T L^-1 n+ (StructuredJ::premultByJt)
+    for(int i = tid; i < n; i += T) w[i] = 0.0;
+    __syncthreads();
+    int hs, he;
+    if(status <= BG_EQUALITY)
+    {
+      const int bi = P.toblock[p];
+      const int rows = P.cnvar[bi], s0 = P.cvar0[bi];
+      const double * c = C + P.coff[bi] + (long long)(p - P.ccstr0[bi]) * P.cld[bi];
+      for(int i = tid; i < rows; i += T) w[pidx(s0 + i)] = c[i];
+      hs = s0;
+      he = s0 + rows;
+    }
+    else
+    {
+      const int b = p - mc;
+      if(tid == 0) w[pidx(b)] = status == BG_UPPER_BOUND ? -1.0 : 1.0;
+      hs = b;
+      he = b + 1;
+    }
+    __syncthreads();
+    sg_solve_inplace(P.G, base, w, Lt, Bt, false, hs, he);
+    const bool neg = status == BG_UPPER;
+    for(int i = tid; i < n; i += T) d[i] = neg ? -w[i] : w[i];
+    __syncthreads();
+    apply_qt(d);
+    // z = L^-T Q [0; d2] (StructuredJ::premultByJ2)
+    for(int i = tid; i < n; i += T) w[i] = i < q ? 0.0 : d[i];
+    __syncthreads();
+    apply_q(w);
+    sg_solve_inplace(P.G, base, w, Lt, Bt, true, 0, -1);
+    for(int i = tid; i < n; i += T) z[i] = w[pidx(i)];
+    __syncthreads();
+    // r = R^-1 d1 (StructuredQR::RSolve): column-oriented back substitution, true division
+    for(int k = tid; k < q; k += T) w[k] = d[k];
+    __syncthreads();
+    for(int k = q - 1; k >= 0; --k)
+    {
+      const double * Rk = Rg + colR(k);
+      const double rk = w[k] / Rk[k];
+      if(tid == 0) r[k] = rk;
+      for(int j = tid; j < k; j += T) w[j] = fma(-rk, Rk[j], w[j]);
+      __syncthreads();
+    }
+  }
+
+  // ---- StructuredQR::add (src/structured/StructuredQR.cpp:72-86); false: the record storage is full
+  __device__ bool add_constraint(int p, int status)
+  {
+    const int len = n - q;
+    if(nrec >= P.max_iter || qoff + len > P.qcap) return false;
+    const double c0 = d[q];
+    const double tailSq = len == 1 ? 0.0 : block_dot32(len - 1, d + q + 1, d + q + 1);
+    double * pe = Qg + qoff;
+    double tau, beta;
+    if(tailSq <= 2.2250738585072014e-308) // (std::numeric_limits<double>::min)()
+    {
+      tau = 0.0;
+      beta = c0;
+      for(int i = 1 + tid; i < len; i += T) pe[i] = 0.0;
+    }
+    else
+    {
+      beta = sqrt(fma(c0, c0, tailSq));
+      if(c0 >= 0.0) beta = -beta;
+      const double den = c0 - beta;
+      for(int i = 1 + tid; i < len; i += T) pe[i] = d[q + i] / den;
+      tau = (beta - c0) / beta;
+    }
+    double * Rq = Rg + colR(q);
+    for(int k = tid; k < q; k += T) Rq[k] = d[k];
+    if(tid == 0)
+    {
+      pe[0] = tau;
+      Rq[q] = beta;
+      rec[3 * nrec] = q;
+      rec[3 * nrec + 1] = len;
+      rec[3 * nrec + 2] = (int)qoff;
+      st[p] = (signed char)status; // DualSolver::addConstraint: A_.activate
+      alist[q] = p;
+    }
+    qoff += len;
+    ++nrec;
+    ++q;
+    __syncthreads();
+    return true;
+  }
+
+  // ---- DualSolver::removeConstraint + StructuredQR::remove (src/DualSolver.cpp:237-244, StructuredQR.cpp:88-103)
+  __device__ bool remove_constraint(int l)
+  {
+    // u.segment(l, q - l) = u.tail(q - l) (u has q + 1 entries); A_.deactivate(l)
+    const int qa = q;
+    __syncthreads();
+    for(int k0 = l; k0 < qa; k0 += T)
+    {
+      const int k = k0 + tid;
+      const double un = k < qa ? u[k + 1] : 0.0;
+      const int an = k + 1 < qa ? alist[k + 1] : -1;
+      const int gone = alist[l];
+      __syncthreads();
+      if(k0 == l && tid == 0) st[gone] = BG_INACTIVE;
+      if(k < qa)
+      {
+        u[k] = un;
+        if(k + 1 < qa) alist[k] = an;
+      }
+      __syncthreads();
+    }
+    --q;
+    const int g = q - l;
+    if(g <= 0) return true; // the last constraint: an empty Givens sequence
+    if(nrec >= P.max_iter || qoff + 2 * g > P.qcap) return false;
+    double * cs = Qg + qoff;
+    for(int i = l; i < q; ++i)
+    {
+      double * Ri = Rg + colR(i);
+      const double * Ri1 = Rg + colR(i + 1);
+      for(int k = tid; k < i; k += T) Ri[k] = Ri1[k];
+      double c, s, rr;
+      bg_make_givens(Ri1[i], Ri1[i + 1], c, s, rr);
+      __syncthreads(); // everybody has read R(i, i+1), R(i+1, i+1)
+      if(tid == 0)
+      {
+        Ri[i] = rr;
+        cs[i - l] = c;
+        cs[g + i - l] = s;
+      }
+      for(int j = i + 2 + tid; j <= q; j += T) // rows i, i+1 of the columns to the right, rotated by Qi^T
+      {
+        double * Rj = Rg + colR(j);
+        const double xi = Rj[i], yi = Rj[i + 1];
+        Rj[i] = fma(c, xi, -(s * yi));
+        Rj[i + 1] = fma(c, yi, s * xi);
+      }
+      __syncthreads();
+    }
+    if(tid == 0)
+    {
+      rec[3 * nrec] = l | (int)0x80000000;
+      rec[3 * nrec + 1] = g;
+      rec[3 * nrec + 2] = (int)qoff;
+    }
+    qoff += 2 * g;
+    ++nrec;
+    __syncthreads();
+    return true;
+  }
+
+  __device__ void write_failure(long long b, int status)
+  {
+    for(int i = tid; i < n; i += T) P.x[b * n + i] = 0.0;
+    if(P.u)
+      for(int i = tid; i < m; i += T) P.u[b * m + i] = 0.0;
+    if(P.act)
+      for(int i = tid; i < m; i += T) P.act[b * m + i] = 0;
+    if(P.alist)
+      for(int i = tid; i < n; i += T) P.alist[b * n + i] = -1;
+    if(tid == 0)
+    {
+      if(P.f) P.f[b] = 0.0;
+      if(P.iters) P.iters[b] = 0;
+      if(P.status) P.status[b] = status;
+      if(P.nact) P.nact[b] = 0;
+      if(P.qdoubles) P.qdoubles[b] = 0;
+    }
+  }
+
+  __device__ void write_result(long long b, int status, int it)
+  {
+    __syncthreads();
+    for(int i = tid; i < n; i += T) P.x[b * n + i] = x[i];
+    if(P.u)
+    {
+      // DualSolver::multipliers (src/DualSolver.cpp:38-69)
+      for(int i = tid; i < m; i += T) P.u[b * m + i] = 0.0;
+      __syncthreads();
+      for(int k = tid; k < q; k += T)
+      {
+        const int i = alist[k];
+        const int s = st[i];
+        P.u[b * m + i] = (s == BG_UPPER || s == BG_UPPER_BOUND) ? u[k] : -u[k];
+      }
+    }
+    if(P.act)
+      for(int i = tid; i < m; i += T) P.act[b * m + i] = st[i];
+    if(P.alist)
+      for(int i = tid; i < n; i += T) P.alist[b * n + i] = i < q ? alist[i] : -1;
+    if(tid == 0)
+    {
+      if(P.f) P.f[b] = f;
+      if(P.iters) P.iters[b] = it;
+      if(P.status) P.status[b] = status;
+      if(P.nact) P.nact[b] = q;
+      if(P.qdoubles) P.qdoubles[b] = qoff;
+    }
+  }
+
+  __device__ void solve(long long b)
+  {
+    base = P.G.data + b * P.G.stride;
+    a = P.a + b * P.sa;
+    C = P.C + b * P.sC;
+    bl = P.bl + b * P.sbl;
+    bu = P.bu + b * P.sbu;
+    xl = P.nb ? P.xl + b * P.sxl : nullptr;
+    xu = P.nb ? P.xu + b * P.sxu : nullptr;
+    q = 0;
+    nrec = 0;
+    qoff = 0;
+    __syncthreads();
+
+    // processInitialActiveSet (src/experimental/BlockGISolver.cpp:293-377), cold start: equalities of the data
+    // would be activated here, and initializePrimalDualPoints asserts there is none (:474)
+    int neq = 0;
+    for(int i = tid; i < m; i += T)
+    {
+      st[i] = BG_INACTIVE;
+      neq += i < mc ? (bl[i] == bu[i]) : (xl[i - mc] == xu[i - mc]);
+    }
+    neq = __syncthreads_count(neq) ? 1 : 0; // (a count of threads; only zero / non-zero and > n matter below)
+    if(neq)
+    {
+      // exact count for the OVERCONSTRAINED test
+      int cnt = 0;
+      if(tid == 0)
+      {
+        for(int i = 0; i < m; ++i) cnt += i < mc ? (bl[i] == bu[i]) : (xl[i - mc] == xu[i - mc]);
+        iscr[8] = cnt;
+      }
+      __syncthreads();
+      cnt = iscr[8];
+      __syncthreads();
+      write_failure(b, cnt > n ? 6 /* OVERCONSTRAINED_PROBLEM */ : 1 /* INCONSISTENT_INPUT */);
+      return;
+    }
+    if(!P.llt_ok[b * P.ok_stride])
+    {
+      write_failure(b, 2 /* NON_POS_HESSIAN */);
+      return;
+    }
+    // initializePrimalDualPoints (:476-481): x = -G^-1 a, f = 0.5 a.x
+    for(int i = tid; i < n; i += T) w[pidx(i)] = a[i];
+    __syncthreads();
+    sg_solve_inplace(P.G, base, w, Lt, Bt, false, 0, -1);
+    sg_solve_inplace(P.G, base, w, Lt, Bt, true, 0, -1);
+    for(int i = tid; i < n; i += T) x[i] = -w[pidx(i)];
+    f = 0.5 * block_dot32(n, a, x);
+
+    // DualSolver::solve (src/DualSolver.cpp:96-168)
+    bool skip1 = false;
+    int p = -1, status = BG_INACTIVE;
+    int it = 0;
+    for(; it < P.max_iter; ++it)
+    {
+      if(!skip1)
+      {
+        p = select(status);
+        if(status == BG_INACTIVE)
+        {
+          write_result(b, 0, it);
+          return;
+        }
+        if(tid == 0) u[q] = 0.0;
+      }
+      compute_step(p, status);
+
+      // computeStepLength_ (src/experimental/BlockGISolver.cpp:176-243)
+      double t1 = P.big_bnd;
+      int l = 0x7fffffff;
+      for(int k = tid; k < q; k += T)
+      {
+        const int sk = st[k]; // the reference indexes the status by the POSITION k (:188), kept
+        if(sk != BG_EQUALITY && sk != BG_FIXED && r[k] > 0.0)
+        {
+          const double tk = u[k] / r[k];
+          if(tk < t1)
+          {
+            t1 = tk;
+            l = k;
+          }
+        }
+      }
+      block_first_min(t1, l);
+      if(l == 0x7fffffff)
+      {
+        t1 = P.big_bnd;
+        l = 0;
+      }
+      const double znorm = sqrt(block_dot32(n, z, z));
+      double t2 = P.big_bnd, ndot = 0.0;
+      if(znorm > 1e-14)
+      {
+        double bnd, cx, cz;
+        if(status <= BG_EQUALITY)
+        {
+          __syncthreads();
+          if(tid == 0) scr[2] = col_dot(p, x);
+          if(tid == T - 1) scr[3] = col_dot(p, z);
+          __syncthreads();
+          cx = scr[2];
+          cz = scr[3];
+          bnd = status == BG_LOWER ? bl[p] : bu[p];
+          ndot = status == BG_UPPER ? -cz : cz;
+        }
+        else
+        {
+          const int pb = p - mc;
+          cx = x[pb];
+          cz = z[pb];
+          bnd = status == BG_LOWER_BOUND ? xl[pb] : xu[pb];
+          ndot = status == BG_UPPER_BOUND ? -cz : cz;
+        }
+        t2 = (bnd - cx) / cz;
+      }
+      const double t = t2 < t1 ? t2 : t1; // std::min(t1, t2)
+      if(t >= P.big_bnd)
+      {
+        write_result(b, 3 /* INFEASIBLE */, it);
+        return;
+      }
+      __syncthreads();
+      if(t2 >= P.big_bnd)
+      {
+        for(int k = tid; k < q; k += T) u[k] = fma(-t, r[k], u[k]);
+        if(tid == 0) u[q] += t;
+        if(!remove_constraint(l))
+        {
+          write_result(b, 7 /* UNKNOWN: record storage exhausted */, it);
+          return;
+        }
+        skip1 = true;
+      }
+      else
+      {
+        for(int i = tid; i < n; i += T) x[i] = fma(t, z[i], x[i]);
+        f += (t * ndot) * (0.5 * t + u[q]);
+        __syncthreads(); // u[q] read by everybody before it changes
+        for(int k = tid; k < q; k += T) u[k] = fma(-t, r[k], u[k]);
+        if(tid == 0) u[q] += t;
+        bool ok;
+        if(t == t2)
+        {
+          ok = add_constraint(p, status);
+          skip1 = false;
+        }
+        else
+        {
+          ok = remove_constraint(l);
+          skip1 = true;
+        }
+        if(!ok)
+        {
+          write_result(b, 7, it);
+          return;
+        }
+      }
+    }
+    write_result(b, 4 /* MAX_ITER_REACHED */, it);
+  }
+};
+
+__global__ void blockgi_kernel(const BlockGiParams P)
+{
+  extern __shared__ __align__(16) double sm[];
+  __shared__ long long next;
+  BlockGi S(P, sm);
+  for(;;)
+  {
+    __syncthreads();
+    if(threadIdx.x == 0) next = (long long)atomicAdd(P.ticket, 1ULL);
+    __syncthreads();
+    const long long b = next;
+    if(b >= P.batch) break;
+    S.solve(b);
+  }
+}
+
+} // namespace jrlqp

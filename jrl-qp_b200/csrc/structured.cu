@@ -1,8 +1,6 @@
 // Host side of the structured-decomposition C-ABI (include/jrlqp_b200.h, jrlqp_structured_*):
 // descriptor upload, launch configuration, and the host-pointer entry points. Pure CUDA runtime.
-#include "structured.cuh"
-
-#include "jrlqp_b200.h"
+#include "structured_host.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -16,43 +14,107 @@ namespace jrlqp
 void count_launch(); // capi.cu: feeds jrlqp_launch_count()
 }
 
-struct jrlqp_structured
+namespace jrlqp
 {
-  int type = 0, b = 0, n = 0, nmax = 0;
-  long long capacity = 0;
-  int device = 0;
-  int threads = 32;
-  int num_sms = 0;
-  int llt_smem = 0, solve_smem = 0, llt_occ = 0, solve_occ = 0;
-  long long touched = 0;
-  std::vector<int> size, dld, old, start;
-  std::vector<long long> doff, ooff;
-  long long min_stride = 0; // one past the last element any block touches
-  // device copies of the descriptor
-  int *d_size = nullptr, *d_dld = nullptr, *d_old = nullptr, *d_start = nullptr;
-  long long *d_doff = nullptr, *d_ooff = nullptr;
-  // staging for the host entry points
-  double * d_data = nullptr;
-  long long d_data_elems = 0;
-  double * d_M = nullptr;
-  long long d_M_elems = 0;
-  int * d_ok = nullptr;
-  cudaStream_t stream = nullptr;
-  std::string err;
 
-  bool check(cudaError_t e, const char * what)
+// ---------------------------------------------------------------------------------------------
+// StructuredG::lltInPlace. Shared memory: 3 tiles of nmax x nmax + nmax doubles of scratch.
+//   tri:   T0 = D_i (current), T1 = S_i, T2 = D_{i+1} (receives the rank update, becomes current)
+//   arrow: T0 = D_i,           T1 = B_i, T2 = D_last  (resident, receives every rank update)
+// ---------------------------------------------------------------------------------------------
+__global__ void structured_llt_kernel(const StructParams P)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int tile = P.nmax * P.nmax;
+  const int b = P.b;
+  const bool tri = P.type == SG_TRI;
+  const bool up = P.type == SG_ARROW_UP;
+  for(long long inst = blockIdx.x; inst < P.batch; inst += gridDim.x)
   {
-    if(e == cudaSuccess) return true;
-    err = std::string(what) + ": " + cudaGetErrorString(e);
-    return false;
+    double * base = P.data + inst * P.stride;
+    double * cur = sm;
+    double * S = sm + tile;
+    double * nxt = sm + 2 * tile;
+    double * vd = sm + 3 * tile;
+    bool ok = true;
+    const int last = up ? 0 : b - 1; // block that ends the permuted system
+    if(tri)
+      load_tile(cur, base + P.doff[0], P.size[0], P.size[0], P.dld[0], false);
+    else
+      load_tile(nxt, base + P.doff[last], P.size[last], P.size[last], P.dld[last], false);
+    for(int i = 0; i < b - 1 && ok; ++i)
+    {
+      const int di = tri ? i : (up ? i + 1 : i); // get<Up>::D(diag, i)
+      const int ni = P.size[di];
+      // off-diagonal block i as stored: tri n_{i+1} x n_i, down n_last x n_i, up n_{i+1} x n_0 (= B_i^T)
+      const int srows = tri ? P.size[i + 1] : (up ? P.size[i + 1] : P.size[last]);
+      const int scols = up ? P.size[0] : ni;
+      const int brows = up ? scols : srows; // rows of B_i once in shared memory (B_i: brows x ni)
+      if(!tri) load_tile(cur, base + P.doff[di], ni, ni, P.dld[di], false);
+      load_tile(S, base + P.ooff[i], srows, scols, P.old[i], up);
+      if(tri) load_tile(nxt, base + P.doff[i + 1], srows, srows, P.dld[i + 1], false);
+      __syncthreads();
+      ok = tile_chol(cur, ni, vd); // Li = chol(Di)
+      if(ok)
+      {
+        tile_trsm_right_lt(S, brows, cur, ni); // Bi = Bi Li^-T
+        __syncthreads();
+        tile_syrk_sub(nxt, brows, S, ni); // D_{i+1} (tri) or D_last (arrow) -= Bi Bi^T
+        store_tile(base + P.doff[di], cur, ni, ni, P.dld[di], false, true);
+        store_tile(base + P.ooff[i], S, srows, scols, P.old[i], up, false);
+      }
+      __syncthreads();
+      if(tri)
+      {
+        double * t = cur;
+        cur = nxt;
+        nxt = t;
+      }
+    }
+    if(ok)
+    {
+      double * Dl = tri ? cur : nxt;
+      const int nl = P.size[last];
+      __syncthreads();
+      ok = tile_chol(Dl, nl, vd);
+      if(ok) store_tile(base + P.doff[last], Dl, nl, nl, P.dld[last], false, true);
+    }
+    if(threadIdx.x == 0 && P.ok) P.ok[inst] = ok ? 1 : 0;
+    __syncthreads();
   }
-};
+}
 
-#define SCK(call)                                       \
-  do                                                    \
-  {                                                     \
-    if(!s->check((call), #call)) return JRLQP_ERR_CUDA; \
-  } while(0)
+// StructuredG::solveL / solveInPlaceLTranspose with the reference's start / end hints.
+// Shared memory: v[n] (the right-hand side / solution), then 2 tiles of nmax x nmax (L_i, B_i).
+__global__ void structured_solve_kernel(const StructParams P)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int n = P.n;
+  double * v = sm;
+  double * Lt = sm + ((n + 1) & ~1);
+  double * Bt = Lt + P.nmax * P.nmax;
+  const bool up = P.type == SG_ARROW_UP;
+  const long long work = P.batch * P.ncols;
+  for(long long w = blockIdx.x; w < work; w += gridDim.x)
+  {
+    const long long inst = w / P.ncols;
+    const int col = (int)(w - inst * P.ncols);
+    const double * base = P.data + inst * P.stride;
+    double * Mc = P.M + inst * P.mstride + (long long)col * P.ldm;
+
+    // load the column (up arrow, L solve: v = P^T m, src/decomposition/blockArrowLLT.cpp:163-169)
+    const bool perm_in = up && !P.transpose;
+    for(int i = threadIdx.x; i < n; i += blockDim.x) v[perm_in ? sg_perm(P, i) : i] = Mc[i];
+    __syncthreads();
+    sg_solve_inplace(P, base, v, Lt, Bt, P.transpose != 0, P.hint_start, P.hint_end);
+    // store (up arrow, L^T solve: m = P v, src/decomposition/blockArrowLLT.cpp:264-270)
+    const bool perm_out = up && P.transpose;
+    for(int i = threadIdx.x; i < n; i += blockDim.x) Mc[i] = v[perm_out ? sg_perm(P, i) : i];
+    __syncthreads();
+  }
+}
+
+} // namespace jrlqp
 
 namespace
 {
@@ -74,31 +136,6 @@ void off_shape(const jrlqp_structured * s, int i, int & rows, int & cols)
     rows = s->size[i + 1];
     cols = s->size[0];
   }
-}
-
-StructParams base_params(const jrlqp_structured * s)
-{
-  StructParams p{};
-  p.type = s->type;
-  p.b = s->b;
-  p.n = s->n;
-  p.nmax = s->nmax;
-  p.size = s->d_size;
-  p.doff = s->d_doff;
-  p.dld = s->d_dld;
-  p.ooff = s->d_ooff;
-  p.old = s->d_old;
-  p.start = s->d_start;
-  return p;
-}
-
-template<class T>
-cudaError_t upload(T *& d, const std::vector<T> & h)
-{
-  cudaError_t e = cudaMalloc(&d, sizeof(T) * std::max<size_t>(h.size(), 1));
-  if(e != cudaSuccess) return e;
-  if(h.empty()) return cudaSuccess;
-  return cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
 }
 
 } // namespace

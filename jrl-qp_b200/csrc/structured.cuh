@@ -146,73 +146,6 @@ __device__ __forceinline__ void tile_syrk_sub(double * D, int n, const double * 
 }
 
 // ---------------------------------------------------------------------------------------------
-// StructuredG::lltInPlace. Shared memory: 3 tiles of nmax x nmax + nmax doubles of scratch.
-//   tri:   T0 = D_i (current), T1 = S_i, T2 = D_{i+1} (receives the rank update, becomes current)
-//   arrow: T0 = D_i,           T1 = B_i, T2 = D_last  (resident, receives every rank update)
-// ---------------------------------------------------------------------------------------------
-__global__ void structured_llt_kernel(const StructParams P)
-{
-  extern __shared__ __align__(16) double sm[];
-  const int tile = P.nmax * P.nmax;
-  const int b = P.b;
-  const bool tri = P.type == SG_TRI;
-  const bool up = P.type == SG_ARROW_UP;
-  for(long long inst = blockIdx.x; inst < P.batch; inst += gridDim.x)
-  {
-    double * base = P.data + inst * P.stride;
-    double * cur = sm;
-    double * S = sm + tile;
-    double * nxt = sm + 2 * tile;
-    double * vd = sm + 3 * tile;
-    bool ok = true;
-    const int last = up ? 0 : b - 1; // block that ends the permuted system
-    if(tri)
-      load_tile(cur, base + P.doff[0], P.size[0], P.size[0], P.dld[0], false);
-    else
-      load_tile(nxt, base + P.doff[last], P.size[last], P.size[last], P.dld[last], false);
-    for(int i = 0; i < b - 1 && ok; ++i)
-    {
-      const int di = tri ? i : (up ? i + 1 : i); // get<Up>::D(diag, i)
-      const int ni = P.size[di];
-      // off-diagonal block i as stored: tri n_{i+1} x n_i, down n_last x n_i, up n_{i+1} x n_0 (= B_i^T)
-      const int srows = tri ? P.size[i + 1] : (up ? P.size[i + 1] : P.size[last]);
-      const int scols = up ? P.size[0] : ni;
-      const int brows = up ? scols : srows; // rows of B_i once in shared memory (B_i: brows x ni)
-      if(!tri) load_tile(cur, base + P.doff[di], ni, ni, P.dld[di], false);
-      load_tile(S, base + P.ooff[i], srows, scols, P.old[i], up);
-      if(tri) load_tile(nxt, base + P.doff[i + 1], srows, srows, P.dld[i + 1], false);
-      __syncthreads();
-      ok = tile_chol(cur, ni, vd); // Li = chol(Di)
-      if(ok)
-      {
-        tile_trsm_right_lt(S, brows, cur, ni); // Bi = Bi Li^-T
-        __syncthreads();
-        tile_syrk_sub(nxt, brows, S, ni); // D_{i+1} (tri) or D_last (arrow) -= Bi Bi^T
-        store_tile(base + P.doff[di], cur, ni, ni, P.dld[di], false, true);
-        store_tile(base + P.ooff[i], S, srows, scols, P.old[i], up, false);
-      }
-      __syncthreads();
-      if(tri)
-      {
-        double * t = cur;
-        cur = nxt;
-        nxt = t;
-      }
-    }
-    if(ok)
-    {
-      double * Dl = tri ? cur : nxt;
-      const int nl = P.size[last];
-      __syncthreads();
-      ok = tile_chol(Dl, nl, vd);
-      if(ok) store_tile(base + P.doff[last], Dl, nl, nl, P.dld[last], false, true);
-    }
-    if(threadIdx.x == 0 && P.ok) P.ok[inst] = ok ? 1 : 0;
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Triangular solves on a vector held in shared memory.
 // ---------------------------------------------------------------------------------------------
 
@@ -247,179 +180,166 @@ __device__ __forceinline__ void vec_gemv_sub(double * w, int rows, TView B, int 
   __syncthreads();
 }
 
-// StructuredG::solveL / solveInPlaceLTranspose with the reference's start / end hints.
-// Shared memory: v[n] (the right-hand side / solution), then 2 tiles of nmax x nmax (L_i, B_i).
-__global__ void structured_solve_kernel(const StructParams P)
+// StructuredG::solveL (transpose = false) / solveInPlaceLTranspose (transpose = true) on a vector v that is
+// already in shared memory, IN THE PERMUTED NUMBERING for the up arrow (sg_perm: the L solve takes v = P^T m,
+// the L^T solve returns m = P v, src/decomposition/blockArrowLLT.cpp:163-169,264-270). start / end are the
+// reference's hints in the caller's numbering (end < 0: none). Lt, Bt: two nmax x nmax tiles of scratch.
+// Every thread of the CTA must call it, after a barrier that makes v visible; ends on a barrier.
+__device__ __forceinline__ int sg_perm(const StructParams & P, int i)
 {
-  extern __shared__ __align__(16) double sm[];
+  const int n0 = P.size[0];
+  return i < n0 ? P.n - n0 + i : i - n0;
+}
+
+__device__ __forceinline__ void sg_solve_inplace(const StructParams & P, const double * base, double * v, double * Lt, double * Bt, bool transpose, int start, int end)
+{
   const int n = P.n, b = P.b;
-  double * v = sm;
-  double * Lt = sm + ((n + 1) & ~1);
-  double * Bt = Lt + P.nmax * P.nmax;
   const bool tri = P.type == SG_TRI;
   const bool up = P.type == SG_ARROW_UP;
   const int n0 = P.size[0];
-  const long long work = P.batch * P.ncols;
-  for(long long w = blockIdx.x; w < work; w += gridDim.x)
+  if(end < 0) end = n;
+  if(tri && !transpose)
   {
-    const long long inst = w / P.ncols;
-    const int col = (int)(w - inst * P.ncols);
-    const double * base = P.data + inst * P.stride;
-    double * Mc = P.M + inst * P.mstride + (long long)col * P.ldm;
-    int start = P.hint_start, end = P.hint_end < 0 ? n : P.hint_end;
-
-    // load the column (up arrow, L solve: v = P^T m, src/decomposition/blockArrowLLT.cpp:163-169)
-    const bool perm_in = up && !P.transpose;
-    for(int i = threadIdx.x; i < n; i += blockDim.x) v[perm_in ? (i < n0 ? n - n0 + i : i - n0) : i] = Mc[i];
-    __syncthreads();
-
-    if(tri && !P.transpose)
+    // triBlockDiagLSolve (src/decomposition/triBlockDiagLLT.cpp:38-98)
+    int nn = 0, l = 0, li = 0;
+    bool zero = true;
+    for(int i = 0; i < b; ++i)
     {
-      // triBlockDiagLSolve (src/decomposition/triBlockDiagLLT.cpp:38-98)
-      int nn = 0, l = 0, li = 0;
-      bool zero = true;
-      for(int i = 0; i < b; ++i)
+      const int ni = P.size[i];
+      if(nn + ni >= start)
       {
-        const int ni = P.size[i];
-        if(nn + ni >= start)
+        load_tile(Lt, base + P.doff[i], ni, ni, P.dld[i], false);
+        if(zero)
         {
-          load_tile(Lt, base + P.doff[i], ni, ni, P.dld[i], false);
-          if(zero)
-          {
-            __syncthreads();
-            const int r = nn + ni - start;
-            vec_solve_lower(TView{Lt, 1, ni}.sub(ni - r, ni - r), r, v + start);
-            zero = false;
-          }
-          else
-          {
-            load_tile(Bt, base + P.ooff[i - 1], ni, li, P.old[i - 1], false);
-            __syncthreads();
-            vec_gemv_sub(v + nn, ni, TView{Bt, 1, ni}, li, v + l);
-            vec_solve_lower(TView{Lt, 1, ni}, ni, v + nn);
-          }
+          __syncthreads();
+          const int r = nn + ni - start;
+          vec_solve_lower(TView{Lt, 1, ni}.sub(ni - r, ni - r), r, v + start);
+          zero = false;
         }
-        l = nn;
-        li = ni;
-        nn += ni;
+        else
+        {
+          load_tile(Bt, base + P.ooff[i - 1], ni, li, P.old[i - 1], false);
+          __syncthreads();
+          vec_gemv_sub(v + nn, ni, TView{Bt, 1, ni}, li, v + l);
+          vec_solve_lower(TView{Lt, 1, ni}, ni, v + nn);
+        }
+      }
+      l = nn;
+      li = ni;
+      nn += ni;
+    }
+  }
+  else if(tri)
+  {
+    // triBlockDiagLTransposeSolve (src/decomposition/triBlockDiagLLT.cpp:100-158)
+    int nn = n, l = 0, li = 0;
+    bool zero = true;
+    for(int i = b - 1; i >= 0; --i)
+    {
+      const int ni = P.size[i];
+      if(nn - ni < end)
+      {
+        load_tile(Lt, base + P.doff[i], ni, ni, P.dld[i], false);
+        if(zero)
+        {
+          __syncthreads();
+          const int r = end - nn + ni;
+          vec_solve_lower_t(TView{Lt, 1, ni}, r, v + nn - ni);
+          zero = false;
+        }
+        else
+        {
+          load_tile(Bt, base + P.ooff[i], li, ni, P.old[i], false); // S_i: n_{i+1} x n_i
+          __syncthreads();
+          vec_gemv_sub(v + nn - ni, ni, TView{Bt, 1, li}.t(), li, v + l - li);
+          vec_solve_lower_t(TView{Lt, 1, ni}, ni, v + nn - ni);
+        }
+      }
+      l = nn;
+      li = ni;
+      nn -= ni;
+    }
+  }
+  else
+  {
+    const int last = up ? 0 : b - 1;
+    const int nl = P.size[last];
+    if(up)
+    {
+      // hints are given in the caller's row numbering; the permuted system starts n0 rows earlier
+      if(!transpose)
+      {
+        start = max(0, start - n0);
+        end = max(0, end - n0);
       }
     }
-    else if(tri)
+    double * vb = v + n - nl; // rows of the last block of the permuted system
+    if(!transpose)
     {
-      // triBlockDiagLTransposeSolve (src/decomposition/triBlockDiagLLT.cpp:100-158)
-      int nn = n, l = 0, li = 0;
-      bool zero = true;
-      for(int i = b - 1; i >= 0; --i)
+      // blockArrowLSolve_ (src/decomposition/blockArrowLLT.cpp:92-152)
+      int nn = 0;
+      for(int i = 0; i < b - 1; ++i)
       {
-        const int ni = P.size[i];
-        if(nn - ni < end)
+        const int di = up ? i + 1 : i;
+        const int ni = P.size[di];
+        const int s = max(start - nn, 0);
+        if(ni < s || end <= nn)
         {
-          load_tile(Lt, base + P.doff[i], ni, ni, P.dld[i], false);
-          if(zero)
-          {
-            __syncthreads();
-            const int r = end - nn + ni;
-            vec_solve_lower_t(TView{Lt, 1, ni}, r, v + nn - ni);
-            zero = false;
-          }
-          else
-          {
-            load_tile(Bt, base + P.ooff[i], li, ni, P.old[i], false); // S_i: n_{i+1} x n_i
-            __syncthreads();
-            vec_gemv_sub(v + nn - ni, ni, TView{Bt, 1, li}.t(), li, v + l - li);
-            vec_solve_lower_t(TView{Lt, 1, ni}, ni, v + nn - ni);
-          }
+          nn += ni;
+          continue;
         }
-        l = nn;
-        li = ni;
-        nn -= ni;
+        const int srows = up ? ni : nl, scols = up ? n0 : ni;
+        load_tile(Lt, base + P.doff[di], ni, ni, P.dld[di], false);
+        load_tile(Bt, base + P.ooff[i], srows, scols, P.old[i], false);
+        __syncthreads();
+        vec_solve_lower(TView{Lt, 1, ni}.sub(s, s), ni - s, v + nn + s);
+        TView B = up ? TView{Bt, 1, srows}.t() : TView{Bt, 1, srows}; // B_i: nl x ni
+        vec_gemv_sub(vb, nl, B.sub(0, s), ni - s, v + nn + s);
+        nn += ni;
       }
+      load_tile(Lt, base + P.doff[last], nl, nl, P.dld[last], false);
+      __syncthreads();
+      vec_solve_lower(TView{Lt, 1, nl}, nl, vb);
     }
     else
     {
-      const int last = up ? 0 : b - 1;
-      const int nl = P.size[last];
-      if(up)
+      // blockArrowLTransposeSolve_ (src/decomposition/blockArrowLLT.cpp:176-252)
+      bool zero = false;
+      if(end > n - nl)
       {
-        // hints are given in the caller's row numbering; the permuted system starts n0 rows earlier
-        if(!P.transpose)
-        {
-          start = max(0, start - n0);
-          end = max(0, end - n0);
-        }
-      }
-      double * vb = v + n - nl; // rows of the last block of the permuted system
-      if(!P.transpose)
-      {
-        // blockArrowLSolve_ (src/decomposition/blockArrowLLT.cpp:92-152)
-        int nn = 0;
-        for(int i = 0; i < b - 1; ++i)
-        {
-          const int di = up ? i + 1 : i;
-          const int ni = P.size[di];
-          const int s = max(start - nn, 0);
-          if(ni < s || end <= nn)
-          {
-            nn += ni;
-            continue;
-          }
-          const int srows = up ? ni : nl, scols = up ? n0 : ni;
-          load_tile(Lt, base + P.doff[di], ni, ni, P.dld[di], false);
-          load_tile(Bt, base + P.ooff[i], srows, scols, P.old[i], false);
-          __syncthreads();
-          vec_solve_lower(TView{Lt, 1, ni}.sub(s, s), ni - s, v + nn + s);
-          TView B = up ? TView{Bt, 1, srows}.t() : TView{Bt, 1, srows}; // B_i: nl x ni
-          vec_gemv_sub(vb, nl, B.sub(0, s), ni - s, v + nn + s);
-          nn += ni;
-        }
+        const int r = end - n + nl;
         load_tile(Lt, base + P.doff[last], nl, nl, P.dld[last], false);
         __syncthreads();
-        vec_solve_lower(TView{Lt, 1, nl}, nl, vb);
+        vec_solve_lower_t(TView{Lt, 1, nl}, r, vb);
       }
       else
+        zero = true;
+      int nn = 0;
+      for(int i = 0; i < b - 1; ++i)
       {
-        // blockArrowLTransposeSolve_ (src/decomposition/blockArrowLLT.cpp:176-252)
-        bool zero = false;
-        if(end > n - nl)
+        const int di = up ? i + 1 : i;
+        const int ni = P.size[di];
+        if(zero && start >= nn + ni)
         {
-          const int r = end - n + nl;
-          load_tile(Lt, base + P.doff[last], nl, nl, P.dld[last], false);
-          __syncthreads();
-          vec_solve_lower_t(TView{Lt, 1, nl}, r, vb);
-        }
-        else
-          zero = true;
-        int nn = 0;
-        for(int i = 0; i < b - 1; ++i)
-        {
-          const int di = up ? i + 1 : i;
-          const int ni = P.size[di];
-          if(zero && start >= nn + ni)
-          {
-            nn += ni;
-            continue;
-          }
-          const int srows = up ? ni : nl, scols = up ? n0 : ni;
-          __syncthreads();
-          if(!zero) load_tile(Bt, base + P.ooff[i], srows, scols, P.old[i], false);
-          if(end >= nn) load_tile(Lt, base + P.doff[di], ni, ni, P.dld[di], false);
-          __syncthreads();
-          if(!zero)
-          {
-            TView B = up ? TView{Bt, 1, srows}.t() : TView{Bt, 1, srows}; // B_i: nl x ni
-            vec_gemv_sub(v + nn, ni, B.t(), nl, vb);
-          }
-          if(end >= nn) vec_solve_lower_t(TView{Lt, 1, ni}, end >= nn + ni ? ni : end - nn, v + nn);
           nn += ni;
+          continue;
         }
+        const int srows = up ? ni : nl, scols = up ? n0 : ni;
+        __syncthreads();
+        if(!zero) load_tile(Bt, base + P.ooff[i], srows, scols, P.old[i], false);
+        if(end >= nn) load_tile(Lt, base + P.doff[di], ni, ni, P.dld[di], false);
+        __syncthreads();
+        if(!zero)
+        {
+          TView B = up ? TView{Bt, 1, srows}.t() : TView{Bt, 1, srows}; // B_i: nl x ni
+          vec_gemv_sub(v + nn, ni, B.t(), nl, vb);
+        }
+        if(end >= nn) vec_solve_lower_t(TView{Lt, 1, ni}, end >= nn + ni ? ni : end - nn, v + nn);
+        nn += ni;
       }
     }
-    __syncthreads();
-    // store (up arrow, L^T solve: m = P v, src/decomposition/blockArrowLLT.cpp:264-270)
-    const bool perm_out = up && P.transpose;
-    for(int i = threadIdx.x; i < n; i += blockDim.x) Mc[i] = v[perm_out ? (i < n0 ? n - n0 + i : i - n0) : i];
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 } // namespace jrlqp

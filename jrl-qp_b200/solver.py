@@ -124,6 +124,8 @@ EXPORTED_SYMBOLS = [
     "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host", "jrlqp_set_kernel_path",
     "jrlqp_solve_sequence_device", "jrlqp_solve_sequence_host",
     "jrlqp_kkt_default_args", "jrlqp_kkt_check_device", "jrlqp_kkt_check_host",
+    "jrlqp_blockgi_create", "jrlqp_blockgi_destroy", "jrlqp_blockgi_last_error", "jrlqp_blockgi_set_options",
+    "jrlqp_blockgi_get_options", "jrlqp_blockgi_solve_device", "jrlqp_blockgi_solve_host", "jrlqp_blockgi_get_info",
 ]
 
 _lib = None

@@ -222,3 +222,50 @@ class StructuredG:
 
     def solveLTranspose(self, v, start=0, end=-1):
         return self._solve(v, True, start, end)
+
+
+class CStructure:
+    """Where the blocks of a block-diagonal constraint matrix live (structured::StructuredC built from a
+    std::vector<MatrixConstRef>, src/structured/StructuredC.cpp:9-25): block i is nvar[i] x ncstr[i], column-major
+    (one constraint normal per column) at element `offset[i]` from the instance base, leading dimension ld[i];
+    `stride` = elements per instance. Constraints are numbered block after block."""
+
+    def __init__(self, nvar, ncstr, offset, ld, stride):
+        self.nvar = np.asarray(nvar, dtype=np.int32)
+        self.ncstr = np.asarray(ncstr, dtype=np.int32)
+        self.offset = np.asarray(offset, dtype=np.int64)
+        self.ld = np.asarray(ld, dtype=np.int32)
+        self.stride = int(stride)
+        self.n = int(self.nvar.sum())
+        self.mc = int(self.ncstr.sum())
+
+    @classmethod
+    def packed(cls, nvar, ncstr):
+        """Blocks stored back to back, ld = rows."""
+        nvar = np.asarray(nvar, dtype=np.int64)
+        ncstr = np.asarray(ncstr, dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(nvar * ncstr)])
+        return cls(nvar, ncstr, off[:-1], nvar, int(off[-1]))
+
+    @classmethod
+    def dense(cls, nvar, ncstr, ld=None):
+        """Blocks are views into a dense column-major n x mc matrix (tests/BlockGISolverTest.in.cpp:90-100)."""
+        nvar = np.asarray(nvar, dtype=np.int64)
+        ncstr = np.asarray(ncstr, dtype=np.int64)
+        n, mc = int(nvar.sum()), int(ncstr.sum())
+        ld = n if ld is None else int(ld)
+        r0 = np.concatenate([[0], np.cumsum(nvar)])[:-1]
+        c0 = np.concatenate([[0], np.cumsum(ncstr)])[:-1]
+        return cls(nvar, ncstr, r0 + c0 * ld, np.full(len(nvar), ld), ld * mc)
+
+    def pack(self, Cd):
+        """Dense [B, mc, n] (row j = normal of constraint j) -> data [B, stride] in this layout."""
+        Cd = np.asarray(Cd, dtype=np.float64)
+        data = np.zeros((Cd.shape[0], self.stride))
+        r0 = np.concatenate([[0], np.cumsum(self.nvar)])
+        c0 = np.concatenate([[0], np.cumsum(self.ncstr)])
+        for i in range(len(self.nvar)):
+            for j in range(int(self.ncstr[i])):
+                o = int(self.offset[i]) + j * int(self.ld[i])
+                data[:, o:o + int(self.nvar[i])] = Cd[:, c0[i] + j, r0[i]:r0[i + 1]]
+        return data

@@ -28,10 +28,12 @@ class BlockProblem:
         self.n, self.mc = stC.n, stC.mc
 
 
-def random_block_problem(type, sizes, mi, batch, seed, bounds=False, active_frac=0.5, layout="packed", shift=0.0):
-    """G = A A^T (tri-block-diagonal) or A^T A (arrow), a ~ U[-1,1]; per block i, m_i double-sided inequalities
-    l <= C_i^T x_i <= u whose feasible set contains a planted point x0 (so the problem is feasible) while the
-    unconstrained minimiser usually violates some of them; optionally box bounds around x0."""
+def random_block_problem(type, sizes, mi, batch, seed, bounds=False, active_frac=0.3, layout="packed", shift=0.0):
+    """G = A A^T (tri-block-diagonal) or A^T A (arrow); per block i, m_i double-sided inequalities
+    l <= C_i^T x_i <= u, optionally box bounds. Built around a planted optimum x* as the reference's generator does
+    (src/test/randomProblems.cpp:150-225): a fraction `active_frac` of the constraints of every block (at most n_i,
+    so that the active normals are independent) is active at x* on a random side with a multiplier in (0, 1],
+    the others are strictly satisfied with slacks |U[-1,1]|, and a = -G x* + sum +/- lambda_j c_j."""
     rng = np.random.default_rng(seed)
     sizes = [int(s) for s in sizes]
     mi = [int(m) for m in mi]
@@ -41,27 +43,37 @@ def random_block_problem(type, sizes, mi, batch, seed, bounds=False, active_frac
     Gdata = stG.pack(H)
     if layout != "packed":  # dense layout: keep the full symmetric matrix in place
         Gdata = np.ascontiguousarray(H.transpose(0, 2, 1).reshape(batch, n * n))
-    a = rng.uniform(-1, 1, (batch, n))
     stC = po.CStructure.packed(sizes, mi) if layout == "packed" else po.CStructure.dense(sizes, mi)
     Cd = np.zeros((batch, mc, n))
     r0 = np.concatenate([[0], np.cumsum(sizes)])
     c0 = np.concatenate([[0], np.cumsum(mi)])
+    act = np.zeros((batch, mc), dtype=bool)
     for i in range(len(sizes)):
         Cd[:, c0[i]:c0[i + 1], r0[i]:r0[i + 1]] = rng.standard_normal((batch, mi[i], sizes[i]))
+        k = min(int(round(active_frac * mi[i])), sizes[i] - (1 if bounds else 0))
+        for b in range(batch):
+            act[b, c0[i] + rng.permutation(mi[i])[:k]] = True
     x0 = rng.uniform(-1, 1, (batch, n))
     cx = np.einsum("bjn,bn->bj", Cd, x0)
-    lo = np.abs(rng.uniform(-1, 1, (batch, mc)))
-    hi = np.abs(rng.uniform(-1, 1, (batch, mc)))
-    tight = rng.uniform(0, 1, (batch, mc)) < active_frac  # narrow some of the slabs so that they end up active
-    lo = np.where(tight, 0.05 * lo, lo)
-    hi = np.where(tight, 0.05 * hi, hi)
+    upper = rng.uniform(0, 1, (batch, mc)) < 0.5
+    lam = np.where(act, 1.0 - rng.uniform(0, 1, (batch, mc)), 0.0)
+    lo = np.where(act & ~upper, 0.0, np.abs(rng.uniform(-1, 1, (batch, mc))) + 1e-3)
+    hi = np.where(act & upper, 0.0, np.abs(rng.uniform(-1, 1, (batch, mc))) + 1e-3)
     bl, bu = cx - lo, cx + hi
+    # stationarity: G x* + a = sum_{lower} lam c - sum_{upper} lam c
+    a = -np.einsum("bij,bj->bi", H, x0) + np.einsum("bjn,bj->bn", Cd, np.where(upper, -lam, lam))
     Cdata = stC.pack(Cd)
     xl = xu = None
     if bounds:
-        xl = x0 - np.abs(rng.uniform(-1, 1, (batch, n))) * 0.5
-        xu = x0 + np.abs(rng.uniform(-1, 1, (batch, n))) * 0.5
-    return BlockProblem(stG, stC, Gdata, a, Cdata, bl, bu, xl, xu, Gdense=H, Cdense=Cd)
+        bact = rng.uniform(0, 1, (batch, n)) < 0.1
+        bup = rng.uniform(0, 1, (batch, n)) < 0.5
+        blam = np.where(bact, 1.0 - rng.uniform(0, 1, (batch, n)), 0.0)
+        xl = x0 - np.where(bact & ~bup, 0.0, np.abs(rng.uniform(-1, 1, (batch, n))) + 1e-3)
+        xu = x0 + np.where(bact & bup, 0.0, np.abs(rng.uniform(-1, 1, (batch, n))) + 1e-3)
+        a = a + np.where(bup, -blam, blam)
+    pb = BlockProblem(stG, stC, Gdata, a, Cdata, bl, bu, xl, xu, Gdense=H, Cdense=Cd)
+    pb.x_planted = x0
+    return pb
 
 
 def dense_solution(pb, nthreads=4):
