@@ -195,6 +195,11 @@ int jrlqp_set_stage_c(jrlqp_solver * s, int32_t mode);
  * 1 = shared-memory kernel (n <= 128), 2 = global-workspace kernel (any n <= 1024; used by the tests
  * to cross-check the two families on the same problems — their results are bit-identical). */
 int jrlqp_set_kernel_path(jrlqp_solver * s, int32_t mode);
+/* Constraint scan of the shared-memory kernels when C is not staged: 1 = every CTA keeps a transposed copy of its
+ * problem's C in a global-memory slice (L2-resident) and scans it with coalesced loads, 0 = scan C in place (one strided
+ * row per thread), -1 (default) = automatic (transposed for n > 64, where it measures faster). Same arithmetic: results
+ * are bit-identical (tests cross-check both). */
+int jrlqp_set_scan_transposed(jrlqp_solver * s, int32_t on);
 /* Number of kernels this library has launched since it was loaded (all solvers). */
 int64_t jrlqp_launch_count(void);
 /* Last CUDA error string seen by this solver ("" if none). */

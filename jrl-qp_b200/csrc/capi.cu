@@ -176,6 +176,12 @@ struct jrlqp_solver
   long long work_stride[2] = {0, 0};
   // capacity (instances) of every staging buffer of the host entry point: 1 for arrays shared by the batch
   long long cap_G = 0, cap_a = 0, cap_C = 0, cap_bl = 0, cap_bu = 0, cap_xl = 0, cap_xu = 0, cap_out = 0, cap_L = 0;
+  // transposed copy of C for the coalesced constraint scan of the non-staged shared-memory kernels
+  int scan_transposed = -1; // 1: scan the CTA's transposed copy of C, 0: scan C in place, -1: automatic (transposed for n > 64)
+  double * d_ct = nullptr;
+  int * d_ct_busy = nullptr;
+  int ct_slots = 0, ldct = 0;
+  long long ct_stride = 0;
   int num_sms = 0;
   int regs = 0;
   int max_smem_optin = 0;
@@ -385,7 +391,7 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_ct, s->d_ct_busy, s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -425,6 +431,13 @@ int jrlqp_set_kernel_path(jrlqp_solver * s, int32_t mode)
   s->wkernel = nullptr;
   cudaSetDevice(s->device);
   return configure_kernel(s);
+}
+
+int jrlqp_set_scan_transposed(jrlqp_solver * s, int32_t on)
+{
+  if(!s || on < -1 || on > 1) return JRLQP_ERR_ARG;
+  s->scan_transposed = on;
+  return JRLQP_OK;
 }
 
 int jrlqp_get_kernel_info(const jrlqp_solver * s, jrlqp_kernel_info * info)
@@ -477,6 +490,32 @@ static int validate(const jrlqp_solver * s, const jrlqp_problem * pb, const jrlq
 
 static int configure_warm(jrlqp_solver * s);
 
+// measured (profiles/r01m_*): the transposed scan pays for wide CTAs (n = 128: +6 %), not for n = 50 (-4 %)
+static bool scan_transposed_on(const jrlqp_solver * s)
+{
+  return s->scan_transposed == 1 || (s->scan_transposed < 0 && s->warps >= 3);
+}
+
+// Slices for the transposed copy of C (gi_dense_cta.cuh: stage_ct): as many as CTAs of the shared-memory kernels
+// (cold and warm, whatever the launch or stream) can be resident at the same time.
+static int ensure_ct(jrlqp_solver * s)
+{
+  if(s->large || s->mc == 0 || !scan_transposed_on(s)) return JRLQP_OK;
+  const int slots = 2 * std::max(s->occ, 1) * s->num_sms;
+  if(s->d_ct && slots <= s->ct_slots) return JRLQP_OK;
+  if(s->d_ct) CK(cudaFree(s->d_ct));
+  if(s->d_ct_busy) CK(cudaFree(s->d_ct_busy));
+  s->d_ct = nullptr;
+  s->d_ct_busy = nullptr;
+  s->ldct = (s->mc + 3) & ~3;
+  s->ct_stride = (((long long)s->n * s->ldct) + 15) & ~15ll;
+  s->ct_slots = slots;
+  CK(cudaMalloc(&s->d_ct_busy, sizeof(int) * (size_t)slots));
+  CK(cudaMemset(s->d_ct_busy, 0, sizeof(int) * (size_t)slots));
+  CK(cudaMalloc(&s->d_ct, sizeof(double) * (size_t)s->ct_stride * (size_t)slots));
+  return JRLQP_OK;
+}
+
 static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter, bool warm = false, bool force_warm_start = false)
 {
   if(s->large)
@@ -489,8 +528,20 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
     int rc = configure_warm(s);
     if(rc != JRLQP_OK) return rc;
   }
+  {
+    int rc = ensure_ct(s);
+    if(rc != JRLQP_OK) return rc;
+  }
   const Layout & lay = warm ? s->wlay : s->lay;
   GiParams p{};
+  if(!s->large && s->mc > 0 && scan_transposed_on(s) && s->d_ct)
+  {
+    p.ct = s->d_ct;
+    p.ct_stride = s->ct_stride;
+    p.ct_busy = s->d_ct_busy;
+    p.ct_slots = s->ct_slots;
+    p.ldct = s->ldct;
+  }
   p.n = s->n;
   p.mc = s->mc;
   p.nb = s->nb;

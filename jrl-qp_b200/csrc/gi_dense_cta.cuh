@@ -178,8 +178,69 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
   {
     // remainder (< CH values): loads first, then the FMAs
     double v[CH];
+    if(VEC)
+    {
 #pragma unroll
-    for(int u = 0; u < CH; ++u) v[u] = k + u < n ? ci[k + u] : 0.0;
+      for(int u = 0; u < CH / 2; ++u)
+      {
+        if(k + 2 * u + 1 < n)
+        {
+          const double2 t = *reinterpret_cast<const double2 *>(ci + k + 2 * u);
+          v[2 * u] = t.x;
+          v[2 * u + 1] = t.y;
+        }
+        else
+        {
+          v[2 * u] = k + 2 * u < n ? ci[k + 2 * u] : 0.0;
+          v[2 * u + 1] = 0.0;
+        }
+      }
+    }
+    else
+    {
+#pragma unroll
+      for(int u = 0; u < CH; ++u) v[u] = k + u < n ? ci[k + u] : 0.0;
+    }
+#pragma unroll
+    for(int u = 0; u < CH / 4; ++u)
+    {
+      if(k + 4 * u < n) c0 = fma(v[4 * u], xs[k + 4 * u], c0);
+      if(k + 4 * u + 1 < n) c1 = fma(v[4 * u + 1], xs[k + 4 * u + 1], c1);
+      if(k + 4 * u + 2 < n) c2 = fma(v[4 * u + 2], xs[k + 4 * u + 2], c2);
+      if(k + 4 * u + 3 < n) c3 = fma(v[4 * u + 3], xs[k + 4 * u + 3], c3);
+    }
+  }
+  return (c0 + c1) + (c2 + c3);
+}
+
+// dot4(ci, x) for one constraint normal read from the TRANSPOSED copy of C (element k of constraint c at
+// Ct[k * ld + c], global memory / L2): consecutive lanes = consecutive constraints read consecutive
+// addresses, so a warp-level load is two full cache lines instead of 32 sectors of 32 different rows.
+// L1 is bypassed (the slice is rewritten by this CTA for every problem).
+template<int CH>
+__device__ __forceinline__ double dot4_col(const double * ci, const long long ld, const double * xs, int n)
+{
+  double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  int k = 0;
+#pragma unroll 1
+  for(; k + CH - 1 < n; k += CH)
+  {
+    double v[CH];
+#pragma unroll
+    for(int u = 0; u < CH; ++u) v[u] = __ldcg(ci + (k + u) * ld);
+#pragma unroll
+    for(int u = 0; u < CH / 4; ++u)
+    {
+      c0 = fma(v[4 * u], xs[k + 4 * u], c0);
+      c1 = fma(v[4 * u + 1], xs[k + 4 * u + 1], c1);
+      c2 = fma(v[4 * u + 2], xs[k + 4 * u + 2], c2);
+      c3 = fma(v[4 * u + 3], xs[k + 4 * u + 3], c3);
+    }
+  }
+  {
+    double v[CH];
+#pragma unroll
+    for(int u = 0; u < CH; ++u) v[u] = k + u < n ? __ldcg(ci + (k + u) * ld) : 0.0;
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
     {
@@ -399,7 +460,25 @@ template<int W, bool STAGE_C, bool WARM = false>
 struct GiCta
 {
   static constexpr int T = 32 * W;
-  static constexpr int CH = W == 1 ? 8 : 16; // values in flight per thread in the constraint scan
+#ifndef JRLQP_OPT_RS
+#  define JRLQP_OPT_RS 0
+#endif
+#ifndef JRLQP_OPT_BS
+#  define JRLQP_OPT_BS 0
+#endif
+#ifndef JRLQP_OPT_ADD
+#  define JRLQP_OPT_ADD 0
+#endif
+#ifndef JRLQP_CH1
+#  define JRLQP_CH1 8
+#endif
+#ifndef JRLQP_CH2
+#  define JRLQP_CH2 16
+#endif
+#ifndef JRLQP_CH4
+#  define JRLQP_CH4 16
+#endif
+  static constexpr int CH = W == 1 ? JRLQP_CH1 : (W == 2 ? JRLQP_CH2 : JRLQP_CH4); // values in flight per thread in the constraint scan
   static constexpr int PF = W == 1 ? 2 : 4; // rotations per chunk when the Givens table is applied
   // ---- immutable per-launch
   const GiParams & P;
@@ -417,6 +496,8 @@ struct GiCta
   const double *Cb, *bl, *bu, *xl, *xu;
   long long ldC; // leading dimension of the constraint-normal storage Cb (staged or global)
   bool cvec; // rows of Cb are 16-byte aligned (128-bit loads allowed)
+  double * Ct = nullptr; // this CTA's slice for the transposed copy of C (null: scan C in place)
+  bool ct_valid = false; // the slice holds the (batch-shared) C already
   // ---- solver state (uniform across threads)
   int q;
   double f;
@@ -462,6 +543,41 @@ struct GiCta
   }
   __device__ __forceinline__ static int colR(int k) { return (k * (k + 1)) >> 1; }
 
+  // Transposed copy of this problem's C into the CTA's global slice (it stays in L2 and is read by every
+  // constraint scan of the solve). C is read once, coalesced (thread = k along a normal), passed through
+  // the J buffer (free until init) as an [constraint][k] tile with odd leading dimension, and written
+  // coalesced (thread = constraint). Called before init() / init_warm().
+  __device__ void stage_ct(long long b)
+  {
+    if(STAGE_C || Ct == nullptr || mc == 0) return;
+    if(P.sC == 0 && ct_valid) return; // C shared by the batch: transposed once per CTA
+    const double * __restrict__ Cg = P.C + b * P.sC;
+    const int ldt = n | 1;
+    const int chunk = max(1, (n * ldj) / ldt);
+    const long long ldct = P.ldct;
+#pragma unroll 1
+    for(int c0 = 0; c0 < mc; c0 += chunk)
+    {
+      const int cn = min(chunk, mc - c0);
+      if(tid < n)
+      {
+#pragma unroll 4
+        for(int c = 0; c < cn; ++c) Jb[c * ldt + tid] = __ldg(Cg + (long long)(c0 + c) * P.ldc + tid);
+      }
+      sync();
+#pragma unroll 1
+      for(int cc = tid; cc < cn; cc += T)
+      {
+        const double * src = Jb + cc * ldt;
+        double * dst = Ct + c0 + cc;
+#pragma unroll 4
+        for(int k = 0; k < n; ++k) __stcg(dst + k * ldct, src[k]);
+      }
+      sync();
+    }
+    ct_valid = true;
+  }
+
   // ------------------------------------------------------------------------------------------
   // init_ (src/GoldfarbIdnaniSolver.cpp:56-82): Cholesky, J = L^-T, x = -G^-1 a, f = a.x/2
   // ------------------------------------------------------------------------------------------
@@ -485,7 +601,7 @@ struct GiCta
       for(int c = 0; c < mc; ++c)
         if(i < n) Cs[c * P.ldcs + i] = __ldg(Cg + i + (long long)c * P.ldc);
     }
-    else if(mc > 0)
+    else if(mc > 0 && Ct == nullptr)
     {
       // pull this problem's C towards L2 while the factorisation runs (it is first needed by the scan)
       const char * Cg = reinterpret_cast<const char *>(P.C + b * P.sC);
@@ -529,12 +645,20 @@ struct GiCta
         {
           Jb[i * ldj + k] = lkk;
           ldiag[k] = lkk;
+#if !JRLQP_OPT_RS
           rs[k] = 1.0 / lkk; // reciprocal of the diagonal for J = L^-T
+#endif
         }
         else if(i > k && i < n)
           Jb[i * ldj + k] = v / lkk;
         sync();
       }
+#if JRLQP_OPT_RS
+      // reciprocals of the diagonal (for J = L^-T and the two triangular solves): one division per thread,
+      // after the loop, instead of one on the critical path of every column
+      if(i < n) rs[i] = 1.0 / ldiag[i];
+      sync();
+#endif
     }
 
     // optional copy-out of L (what the reference leaves in G)
@@ -1201,7 +1325,11 @@ struct GiCta
       if(__ballot_sync(JRLQP_FULL, act) == 0u) continue; // warp-uniform
       const double * ci = Cb + (long long)min(c, mc - 1) * ldC;
       const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
-      const double cx = (!STAGE_C && cvec) ? dot4_row<true, CH>(ci, xs, n) : dot4_row<false, CH>(ci, xs, n);
+      double cx;
+      if(!STAGE_C && Ct != nullptr)
+        cx = dot4_col<CH>(Ct + min(c, mc - 1), P.ldct, xs, n);
+      else
+        cx = (!STAGE_C && cvec) ? dot4_row<true, CH>(ci, xs, n) : dot4_row<false, CH>(ci, xs, n);
       if(act)
       {
         double sl = cx - blc;
@@ -1398,6 +1526,34 @@ struct GiCta
 #pragma unroll
         for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
       }
+#if JRLQP_OPT_BS
+      // the operands of link k - 1 (column k - 1 of R, its diagonal and reciprocal) are loaded before the
+      // dependent part of link k: their shared-memory latency is off the chain
+      double rkk_n = 0.0, ri_n = 0.0, col_n[W];
+      {
+        const int k0 = max(q - 1, 0);
+        const double * R0 = Rp + colR(k0);
+        rkk_n = R0[k0];
+        ri_n = rinv[k0];
+#pragma unroll
+        for(int s = 0; s < W; ++s) col_n[s] = R0[min(lane + 32 * s, k0)];
+      }
+#pragma unroll 2
+      for(int k = q - 1; k >= 0; --k)
+      {
+        const double rkk = rkk_n, ri = ri_n;
+        double col[W];
+#pragma unroll
+        for(int s = 0; s < W; ++s) col[s] = col_n[s];
+        {
+          const int kn = max(k - 1, 0);
+          const double * Rn = Rp + colR(kn);
+          rkk_n = Rn[kn];
+          ri_n = rinv[kn];
+#pragma unroll
+          for(int s = 0; s < W; ++s) col_n[s] = Rn[min(lane + 32 * s, kn)];
+        }
+#else
 #pragma unroll 1
       for(int k = q - 1; k >= 0; --k)
       {
@@ -1406,6 +1562,7 @@ struct GiCta
         double col[W];
 #pragma unroll
         for(int s = 0; s < W; ++s) col[s] = Rk[min(lane + 32 * s, k)];
+#endif
         const double wk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31);
         double rk;
         if(pass == 0)
@@ -1581,6 +1738,49 @@ struct GiCta
         double y = Jr[n - 1];
         int i = n - 2;
         const int lo = q - 1;
+#if JRLQP_OPT_ADD
+        // chunks of PF rotations, two register sets (A, B) used alternately: the operands of the next chunk are
+        // loaded BEFORE the results of the current one are stored (the compiler cannot move a load above a store it
+        // cannot disambiguate), and no register is copied from one set to the other
+        double xa[PF], xb[PF];
+        double2 ca[PF], cb[PF];
+#  define JRLQP_ROT_LOAD(X, Cc, at)            \
+    _Pragma("unroll") for(int u = 0; u < PF; ++u) \
+    {                                          \
+      X[u] = Jr[(at) - u];                     \
+      Cc[u] = gcs[(at) - u];                   \
+    }
+#  define JRLQP_ROT_APPLY(X, Cc)                               \
+    {                                                          \
+      double o[PF];                                            \
+      _Pragma("unroll") for(int u = 0; u < PF; ++u)            \
+      {                                                        \
+        const double c = Cc[u].x, sn = Cc[u].y, xi = X[u];     \
+        o[u] = fma(c, y, sn * xi);                             \
+        y = fma(c, xi, -(sn * y));                             \
+      }                                                        \
+      _Pragma("unroll") for(int u = 0; u < PF; ++u) Jr[i - u + 1] = o[u]; \
+      i -= PF;                                                 \
+    }
+        if(i - (PF - 1) >= lo)
+        {
+          JRLQP_ROT_LOAD(xa, ca, i)
+#pragma unroll 1
+          for(;;)
+          {
+            const bool moreB = i - (2 * PF - 1) >= lo;
+            if(moreB) { JRLQP_ROT_LOAD(xb, cb, i - PF) }
+            JRLQP_ROT_APPLY(xa, ca)
+            if(!moreB) break;
+            const bool moreA = i - (2 * PF - 1) >= lo;
+            if(moreA) { JRLQP_ROT_LOAD(xa, ca, i - PF) }
+            JRLQP_ROT_APPLY(xb, cb)
+            if(!moreA) break;
+          }
+        }
+#  undef JRLQP_ROT_LOAD
+#  undef JRLQP_ROT_APPLY
+#else
         // chunks of PF rotations; the operands of the next chunk are loaded BEFORE the results of the
         // current one are stored (the compiler cannot move a load above a store it cannot disambiguate)
         double xv[PF];
@@ -1630,6 +1830,7 @@ struct GiCta
             }
           }
         }
+#endif
 #pragma unroll 1
         for(; i >= lo; --i)
         {
@@ -1759,6 +1960,7 @@ struct GiCta
     cvec = ((reinterpret_cast<unsigned long long>(Cb) & 15ull) == 0ull) && ((ldC & 1) == 0);
 
     PH_DECL;
+    stage_ct(b);
     int it = 0;
     int cursor = 0; // next constraint / bound to test for pre-activation; m when that phase is over
     if(WARM)
@@ -2006,6 +2208,22 @@ __global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? 16 : (W == 2 ? 6
   extern __shared__ __align__(16) double smem[];
   GiCta<W, STAGE_C, WARM> cta(p, smem);
   unsigned long long * ticket = reinterpret_cast<unsigned long long *>(smem + p.off_scr + 12);
+  int ct_slot = -1;
+  if(!STAGE_C && p.ct != nullptr && p.mc > 0)
+  {
+    // claim a slice for the transposed copy of C (as many slices as CTAs of these kernels can be resident)
+    if(threadIdx.x == 0)
+    {
+      int i = (int)(blockIdx.x % (unsigned)p.ct_slots);
+      while(atomicCAS(p.ct_busy + i, 0, 1) != 0) i = i + 1 == p.ct_slots ? 0 : i + 1;
+      __threadfence();
+      *ticket = (unsigned long long)i;
+    }
+    cta.sync();
+    ct_slot = (int)*ticket;
+    cta.Ct = p.ct + (long long)ct_slot * p.ct_stride;
+    cta.sync();
+  }
   for(;;)
   {
     if(threadIdx.x == 0) *ticket = atomicAdd(p.counter, 1ull);
@@ -2014,6 +2232,11 @@ __global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? 16 : (W == 2 ? 6
     if(b >= (unsigned long long)p.batch) break;
     cta.solve((long long)b);
     cta.sync();
+  }
+  if(ct_slot >= 0 && threadIdx.x == 0)
+  {
+    __threadfence();
+    atomicExch(p.ct_busy + ct_slot, 0);
   }
 }
 

@@ -70,6 +70,13 @@ struct GiParams
   long long work_stride;
   int * work_busy; // one flag per slice: a CTA claims a free slice when it starts and releases it when it exits
   int work_slots;
+  // transposed copy of C for the coalesced constraint scan (gi_dense_cta.cuh, non-staged kernels): one slice of
+  // ct_stride doubles (n rows of ldct) per resident CTA, claimed like the work slices; null = scan C in place
+  double * ct;
+  long long ct_stride;
+  int * ct_busy;
+  int ct_slots;
+  int ldct;
   // persistent work queue
   unsigned long long * counter;
   unsigned long long * phase_cycles; // [4 warps][16 phases], only with -DJRLQP_PHASE_TIMING (else null)

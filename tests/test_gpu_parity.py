@@ -23,9 +23,11 @@ def _oracle(pb, **kw):
     return po.solve_batch(pb.G, pb.a, pb.C, pb.bl, pb.bu, pb.xl, pb.xu, nthreads=os.cpu_count(), **kw)
 
 
-def _gpu(pb, stage=-1, max_iter=None, big_bnd=None, want_L=False):
+def _gpu(pb, stage=-1, max_iter=None, big_bnd=None, want_L=False, scan_transposed=None):
     sv = S.BatchedGoldfarbIdnaniSolver(pb.n, pb.mc, pb.xl is not None, pb.batch)
     sv.set_stage_c(stage)
+    if scan_transposed is not None:
+        sv.set_scan_transposed(scan_transposed)
     if max_iter is not None or big_bnd is not None:
         o = S.SolverOptions()
         if max_iter is not None:
@@ -84,6 +86,21 @@ def test_baseline_configs(cfg, B, stage):
     assert_parity(g, _oracle(pb))
     assert (g["status"] == 0).all()
     assert P.test_kkt(g["x"], g["u"], pb).all()
+
+
+@pytest.mark.parametrize("ch,B", [(P.config_A(), 3000), (P.config_D(), 300), (P.config_B(), 5000),
+                                  (P.ProblemCharacteristics(70, 5, 150, nStrongActIneq=20, bounds=True, nStrongActBounds=5,
+                                                            doubleSidedIneq=True), 500),
+                                  (P.ProblemCharacteristics(33, 3, 7, nStrongActIneq=2), 700)])
+def test_constraint_scan_transposed_copy_and_in_place_agree(ch, B):
+    """C not staged: the scan over the CTA's transposed copy of C (default) and the in-place scan are the same
+    arithmetic; both bit-identical to the oracle (mc > n, mc < n, every CTA width, more problems than slices)."""
+    pb = P.random_problems(ch, B, seed=4242)
+    ref = _oracle(pb)
+    gt = _gpu(pb, stage=0, scan_transposed=True)
+    gi = _gpu(pb, stage=0, scan_transposed=False)
+    assert_parity(gt, ref)
+    assert_parity(gi, ref)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 63, 64, 65, 96, 97, 127])
@@ -193,6 +210,9 @@ def test_shared_hessian_and_constraints_stride_zero():
     sh = P.ProblemBatch(pb.G[0], a, pb.C[0], pb.bl[0], pb.bu[0], pb.xl[0], pb.xu[0])
     ref = po.solve_batch(sh.G, sh.a, sh.C, sh.bl, sh.bu, sh.xl, sh.xu)
     sv = S.BatchedGoldfarbIdnaniSolver(pb.n, pb.mc, True, 300)
+    sv.solve(sh.G, sh.a, sh.C, sh.bl, sh.bu, sh.xl, sh.xu)
+    assert_parity(sv.last, ref)
+    sv.set_stage_c(0)  # C read from global memory: the shared C is transposed once per CTA and re-used
     sv.solve(sh.G, sh.a, sh.C, sh.bl, sh.bu, sh.xl, sh.xu)
     assert_parity(sv.last, ref)
 
