@@ -77,6 +77,7 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage, bool warm = fal
   int o = n * L.ldj;
   L.off_R = o;
   o += n * (n + 1) / 2;
+  o += o & 1; // the vectors start 16-byte aligned (128-bit loads of broadcast operands)
   L.off_x = o;
   o += np;
   L.off_z = o;

@@ -143,8 +143,10 @@ __device__ __noinline__ double dot4_uniform(int len, const double * __restrict__
 // walks its own row, so the loads of a chunk are issued together — CH values in flight per thread,
 // as 128-bit loads when the rows are 16-byte aligned — instead of one round trip per 4 values).
 template<bool VEC, int CH>
-__device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const double * xs, int n)
+__device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const double * xs, int n, const bool act = true)
 {
+  // act == false (constraint already active, or past the last one): the lane issues no memory request at all
+  if(!act) ci = nullptr;
   double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   int k = 0;
 #pragma unroll 1
@@ -156,7 +158,8 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
 #pragma unroll
       for(int u = 0; u < CH / 2; ++u)
       {
-        const double2 t = *reinterpret_cast<const double2 *>(ci + k + 2 * u);
+        double2 t = make_double2(0.0, 0.0);
+        if(ci != nullptr) t = *reinterpret_cast<const double2 *>(ci + k + 2 * u);
         v[2 * u] = t.x;
         v[2 * u + 1] = t.y;
       }
@@ -164,15 +167,25 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
     else
     {
 #pragma unroll
-      for(int u = 0; u < CH; ++u) v[u] = ci[k + u];
+      for(int u = 0; u < CH; ++u) v[u] = ci != nullptr ? ci[k + u] : 0.0;
     }
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
     {
+#if JRLQP_OPT_V2
+      // xs is 16-byte aligned and k + 4 u even: two 128-bit broadcast loads instead of four 64-bit ones
+      const double2 x01 = *reinterpret_cast<const double2 *>(xs + k + 4 * u);
+      const double2 x23 = *reinterpret_cast<const double2 *>(xs + k + 4 * u + 2);
+      c0 = fma(v[4 * u], x01.x, c0);
+      c1 = fma(v[4 * u + 1], x01.y, c1);
+      c2 = fma(v[4 * u + 2], x23.x, c2);
+      c3 = fma(v[4 * u + 3], x23.y, c3);
+#else
       c0 = fma(v[4 * u], xs[k + 4 * u], c0);
       c1 = fma(v[4 * u + 1], xs[k + 4 * u + 1], c1);
       c2 = fma(v[4 * u + 2], xs[k + 4 * u + 2], c2);
       c3 = fma(v[4 * u + 3], xs[k + 4 * u + 3], c3);
+#endif
     }
   }
   {
@@ -183,7 +196,7 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
 #pragma unroll
       for(int u = 0; u < CH / 2; ++u)
       {
-        if(k + 2 * u + 1 < n)
+        if(k + 2 * u + 1 < n && ci != nullptr)
         {
           const double2 t = *reinterpret_cast<const double2 *>(ci + k + 2 * u);
           v[2 * u] = t.x;
@@ -191,7 +204,7 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
         }
         else
         {
-          v[2 * u] = k + 2 * u < n ? ci[k + 2 * u] : 0.0;
+          v[2 * u] = (k + 2 * u < n && ci != nullptr) ? ci[k + 2 * u] : 0.0;
           v[2 * u + 1] = 0.0;
         }
       }
@@ -199,7 +212,7 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
     else
     {
 #pragma unroll
-      for(int u = 0; u < CH; ++u) v[u] = k + u < n ? ci[k + u] : 0.0;
+      for(int u = 0; u < CH; ++u) v[u] = (k + u < n && ci != nullptr) ? ci[k + u] : 0.0;
     }
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
@@ -218,7 +231,7 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
 // addresses, so a warp-level load is two full cache lines instead of 32 sectors of 32 different rows.
 // L1 is bypassed (the slice is rewritten by this CTA for every problem).
 template<int CH>
-__device__ __forceinline__ double dot4_col(const double * ci, const long long ld, const double * xs, int n)
+__device__ __forceinline__ double dot4_col(const double * ci, const long long ld, const double * xs, int n, const bool act = true)
 {
   double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   int k = 0;
@@ -227,7 +240,7 @@ __device__ __forceinline__ double dot4_col(const double * ci, const long long ld
   {
     double v[CH];
 #pragma unroll
-    for(int u = 0; u < CH; ++u) v[u] = __ldcg(ci + (k + u) * ld);
+    for(int u = 0; u < CH; ++u) v[u] = act ? __ldcg(ci + (k + u) * ld) : 0.0;
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
     {
@@ -240,7 +253,7 @@ __device__ __forceinline__ double dot4_col(const double * ci, const long long ld
   {
     double v[CH];
 #pragma unroll
-    for(int u = 0; u < CH; ++u) v[u] = k + u < n ? __ldcg(ci + (k + u) * ld) : 0.0;
+    for(int u = 0; u < CH; ++u) v[u] = (k + u < n && act) ? __ldcg(ci + (k + u) * ld) : 0.0;
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
     {
@@ -259,6 +272,41 @@ __device__ __forceinline__ double dot4_col(const double * ci, const long long ld
 // does not feed the recurrence: it is evaluated afterwards, one rotation per lane.
 // Free function (one warp, lane = threadIdx.x & 31) shared by the shared-memory kernel and the
 // global-workspace kernel (gi_large.cuh).
+// (c, s) of rotation i from what the recurrence stashed: (t, u) and the branch taken in makeGivens
+__device__ __forceinline__ double2 givens_cs(const int kind, const double a, const double u)
+{
+  double c, sn;
+  if(kind == 0)
+  {
+    c = a < 0.0 ? -1.0 : 1.0;
+    sn = 0.0;
+  }
+  else if(kind == 1)
+  {
+    c = 0.0;
+    sn = a < 0.0 ? 1.0 : -1.0;
+  }
+  else
+  {
+    // kind 2: c = 1/u, s = -t c ; kind 3: s = -1/u, c = -t s  (-1/u == -(1/u) exactly)
+    const double inv = 1.0 / u;
+    if(kind == 2)
+    {
+      c = inv;
+      sn = -a * c;
+    }
+    else
+    {
+      sn = -inv;
+      c = -a * sn;
+    }
+  }
+  return make_double2(c, sn);
+}
+
+// SPLIT: the lane-parallel parts on either side of the recurrence (the reciprocals 1 / d[i] before it, the
+// (c, s) pairs after it) are done by the caller with all the threads of the CTA, off this warp's critical path.
+template<bool SPLIT = false>
 __device__ __forceinline__ void givens_chain(const int q, const int n, const int lane, const double * ds, double2 * gcs, double * gc, double * gs, int * gk, double * scr)
 {
   // Latency of one link is what matters here. Per link, Eigen's makeGivens needs t = num / den,
@@ -271,9 +319,15 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
   //  * every other case (|d[i]| > |rho|, a zero operand, proof declined) leaves the straight-line
   //    fast path through one branch and is evaluated with precomputed 1 / d[i] or literally.
   double * rpv = reinterpret_cast<double *>(gcs); // 1 / d[i]; gcs is only written after the chain
+  if(!SPLIT)
+  {
 #pragma unroll 1
-  for(int i = q + lane; i <= n - 1; i += 32) rpv[i] = 1.0 / ds[i];
-  __syncwarp();
+    for(int i = q + lane; i <= n - 1; i += 32)
+    {
+      rpv[i] = 1.0 / ds[i];
+    }
+    __syncwarp();
+  }
   double rho = ds[n - 1];
   double rrR = rpv[n - 1]; // reciprocal of rho, refined
   double rrE = rrR; // reciprocal of rho available before rho itself (feeds q0 and the correction)
@@ -300,7 +354,11 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
     const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
     const double tol = fabs(rho) * hu;
     const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
+#ifdef JRLQP_DIAG_NOPROOF
+    const bool fast = fabs(p) <= fabs(rho) && p != 0.0; // DIAGNOSTIC ONLY (not exact): cost of the proof on the chain
+#else
     const bool fast = fabs(e2) < tol && tol > 1e-270 && !pow2 && fabs(p) <= fabs(rho) && p != 0.0;
+#endif
     if(!fast)
     {
       const double rp = rpv[i];
@@ -350,41 +408,15 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
   }
   if(lane == 0) scr[11] = rrR; // ~ 1 / rho: reciprocal of the new diagonal entry of R
   if(lane == 0) scr[10] = rho;
-  __syncwarp();
-#pragma unroll 1
-  for(int i = q + lane; i <= n - 2; i += 32)
+  if(!SPLIT)
   {
-    const int kind = gk[i];
-    const double a = gc[i];
-    double c, sn;
-    if(kind == 0)
+    __syncwarp();
+#pragma unroll 1
+    for(int i = q + lane; i <= n - 2; i += 32)
     {
-      c = a < 0.0 ? -1.0 : 1.0;
-      sn = 0.0;
+      gcs[i] = givens_cs(gk[i], gc[i], gs[i]);
     }
-    else if(kind == 1)
-    {
-      c = 0.0;
-      sn = a < 0.0 ? 1.0 : -1.0;
-    }
-    else
-    {
-      // kind 2: c = 1/u, s = -t c ; kind 3: s = -1/u, c = -t s  (-1/u == -(1/u) exactly)
-      const double inv = 1.0 / gs[i];
-      if(kind == 2)
-      {
-        c = inv;
-        sn = -a * c;
-      }
-      else
-      {
-        sn = -inv;
-        c = -a * sn;
-      }
-    }
-    gcs[i] = make_double2(c, sn);
   }
-
 }
 
 struct Sel
@@ -461,25 +493,44 @@ struct GiCta
 {
   static constexpr int T = 32 * W;
 #ifndef JRLQP_OPT_RS
-#  define JRLQP_OPT_RS 0
+#  define JRLQP_OPT_RS 1
 #endif
-#ifndef JRLQP_OPT_BS
-#  define JRLQP_OPT_BS 0
+#ifndef JRLQP_OPT_V2
+#  define JRLQP_OPT_V2 1
+#endif
+#ifndef JRLQP_OPT_PRED
+#  define JRLQP_OPT_PRED 1
+#endif
+#ifndef JRLQP_OPT_CS
+#  define JRLQP_OPT_CS 1
 #endif
 #ifndef JRLQP_OPT_ADD
-#  define JRLQP_OPT_ADD 0
+#  define JRLQP_OPT_ADD 1
 #endif
 #ifndef JRLQP_CH1
-#  define JRLQP_CH1 8
+#  define JRLQP_CH1 4
 #endif
 #ifndef JRLQP_CH2
-#  define JRLQP_CH2 16
+#  define JRLQP_CH2 8
 #endif
 #ifndef JRLQP_CH4
 #  define JRLQP_CH4 16
 #endif
   static constexpr int CH = W == 1 ? JRLQP_CH1 : (W == 2 ? JRLQP_CH2 : JRLQP_CH4); // values in flight per thread in the constraint scan
-  static constexpr int PF = W == 1 ? 2 : 4; // rotations per chunk when the Givens table is applied
+#ifndef JRLQP_PF1
+#  define JRLQP_PF1 2
+#endif
+#ifndef JRLQP_PF4
+#  define JRLQP_PF4 4
+#endif
+#ifndef JRLQP_UNR_DZ
+#  define JRLQP_UNR_DZ 2
+#endif
+#ifndef JRLQP_PF2
+#  define JRLQP_PF2 2
+#endif
+  static constexpr int UNR_DZ = JRLQP_UNR_DZ; // unroll factor of the d = J^T n+ and z = J2 d2 loops
+  static constexpr int PF = W == 1 ? JRLQP_PF1 : (W == 2 ? JRLQP_PF2 : JRLQP_PF4); // rotations per chunk when the Givens table is applied
   // ---- immutable per-launch
   const GiParams & P;
   const int tid, lane, warp;
@@ -1309,8 +1360,15 @@ struct GiCta
   // unchanged between the two when step 1 was executed; same dot4 => same bits).
   // ------------------------------------------------------------------------------------------
   // TW = number of warps taking part (W: whole CTA, barriers allowed).
+#ifndef JRLQP_SELECT_INLINE
+#  define JRLQP_SELECT_INLINE 1
+#endif
   template<int TW>
+#if JRLQP_SELECT_INLINE
   __device__ __forceinline__ Sel select(double & cx_sel)
+#else
+  __device__ __noinline__ Sel select(double & cx_sel)
+#endif
   {
     constexpr int TT = 32 * TW;
     const int tt = TW == 1 ? lane : tid;
@@ -1327,9 +1385,9 @@ struct GiCta
       const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
       double cx;
       if(!STAGE_C && Ct != nullptr)
-        cx = dot4_col<CH>(Ct + min(c, mc - 1), P.ldct, xs, n);
+        cx = dot4_col<CH>(Ct + min(c, mc - 1), P.ldct, xs, n, JRLQP_OPT_PRED ? act : true);
       else
-        cx = (!STAGE_C && cvec) ? dot4_row<true, CH>(ci, xs, n) : dot4_row<false, CH>(ci, xs, n);
+        cx = (!STAGE_C && cvec) ? dot4_row<true, CH>(ci, xs, n, JRLQP_OPT_PRED ? act : true) : dot4_row<false, CH>(ci, xs, n, JRLQP_OPT_PRED ? act : true);
       if(act)
       {
         double sl = cx - blc;
@@ -1454,13 +1512,22 @@ struct GiCta
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const double * Jc = Jb + jc;
       int i = 0;
-#pragma unroll 2
+#pragma unroll UNR_DZ
       for(; i + 3 < n; i += 4)
       {
+#if JRLQP_OPT_V2
+        const double2 c01 = *reinterpret_cast<const double2 *>(cv + i);
+        const double2 c23 = *reinterpret_cast<const double2 *>(cv + i + 2);
+        a0 = fma(Jc[i * ldj], c01.x, a0);
+        a1 = fma(Jc[(i + 1) * ldj], c01.y, a1);
+        a2 = fma(Jc[(i + 2) * ldj], c23.x, a2);
+        a3 = fma(Jc[(i + 3) * ldj], c23.y, a3);
+#else
         a0 = fma(Jc[i * ldj], cv[i], a0);
         a1 = fma(Jc[(i + 1) * ldj], cv[i + 1], a1);
         a2 = fma(Jc[(i + 2) * ldj], cv[i + 2], a2);
         a3 = fma(Jc[(i + 3) * ldj], cv[i + 3], a3);
+#endif
       }
       if(i < n) a0 = fma(Jc[i * ldj], cv[i], a0);
       if(i + 1 < n) a1 = fma(Jc[(i + 1) * ldj], cv[i + 1], a1);
@@ -1482,7 +1549,7 @@ struct GiCta
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const double * Jr = Jb + jc * ldj;
       int c = q;
-#pragma unroll 2
+#pragma unroll UNR_DZ
       for(; c + 3 < n; c += 4)
       {
         a0 = fma(Jr[c], ds[c], a0);
@@ -1494,6 +1561,12 @@ struct GiCta
       if(c + 1 < n) a1 = fma(Jr[c + 1], ds[c + 1], a1);
       if(c + 2 < n) a2 = fma(Jr[c + 2], ds[c + 2], a2);
       if(j < n) zs[j] = (a0 + a1) + (a2 + a3);
+      // 1 / d[j] for the fall-back branches of the Givens recurrence: one division per thread here, overlapped with
+      // the dot product above, instead of a lane-parallel pass at the head of the recurrence on warp 1
+      if(SPLIT_CHAIN && j >= q && j < n)
+      {
+        reinterpret_cast<double *>(gcs)[j] = 1.0 / ds[j];
+      }
     }
 
     // the two serial recurrences, concurrently on different warps when W > 1
@@ -1526,34 +1599,8 @@ struct GiCta
 #pragma unroll
         for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
       }
-#if JRLQP_OPT_BS
-      // the operands of link k - 1 (column k - 1 of R, its diagonal and reciprocal) are loaded before the
-      // dependent part of link k: their shared-memory latency is off the chain
-      double rkk_n = 0.0, ri_n = 0.0, col_n[W];
-      {
-        const int k0 = max(q - 1, 0);
-        const double * R0 = Rp + colR(k0);
-        rkk_n = R0[k0];
-        ri_n = rinv[k0];
-#pragma unroll
-        for(int s = 0; s < W; ++s) col_n[s] = R0[min(lane + 32 * s, k0)];
-      }
-#pragma unroll 2
-      for(int k = q - 1; k >= 0; --k)
-      {
-        const double rkk = rkk_n, ri = ri_n;
-        double col[W];
-#pragma unroll
-        for(int s = 0; s < W; ++s) col[s] = col_n[s];
-        {
-          const int kn = max(k - 1, 0);
-          const double * Rn = Rp + colR(kn);
-          rkk_n = Rn[kn];
-          ri_n = rinv[kn];
-#pragma unroll
-          for(int s = 0; s < W; ++s) col_n[s] = Rn[min(lane + 32 * s, kn)];
-        }
-#else
+      // (prefetching the operands of link k - 1 ahead of the dependent part of link k was measured twice — with a
+      // rotating register set, -9 % at n = 50, and with two alternating sets, -6 %: profiles/r01n_ab_A.txt, r01o_ab_A.txt)
 #pragma unroll 1
       for(int k = q - 1; k >= 0; --k)
       {
@@ -1562,7 +1609,6 @@ struct GiCta
         double col[W];
 #pragma unroll
         for(int s = 0; s < W; ++s) col[s] = Rk[min(lane + 32 * s, k)];
-#endif
         const double wk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31);
         double rk;
         if(pass == 0)
@@ -1591,7 +1637,8 @@ struct GiCta
   }
 
   // Givens recurrence of the add that may follow (see givens_chain above)
-  __device__ __forceinline__ void givens_recurrence() { givens_chain(q, n, lane, ds, gcs, gc, gs, gk, scr); }
+  static constexpr bool SPLIT_CHAIN = JRLQP_OPT_CS && W > 1;
+  __device__ __forceinline__ void givens_recurrence() { givens_chain<SPLIT_CHAIN>(q, n, lane, ds, gcs, gc, gs, gk, scr); }
 
   // ------------------------------------------------------------------------------------------
   // computeStepLength_ (src/GoldfarbIdnaniSolver.cpp:150-219), incl. the activationStatus(k) quirk.
@@ -2109,6 +2156,12 @@ struct GiCta
       have_sel = dec[5] != 0;
       if(add)
       {
+        if(SPLIT_CHAIN)
+        {
+          // the (c, s) pairs of the sweep, one rotation per thread (second division of makeGivens)
+          if(tid >= q && tid <= n - 2) gcs[tid] = givens_cs(gk[tid], gc[tid], gs[tid]);
+          if(!have_sel) sync(); // otherwise the barrier inside select() publishes the table
+        }
         // x and the active set are final: the next violated constraint can be selected now, by the
         // whole CTA, before the rotations are applied (they do not touch x)
         Sel nxt{-1, ST_INACTIVE};
