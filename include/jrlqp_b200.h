@@ -200,6 +200,12 @@ int jrlqp_set_kernel_path(jrlqp_solver * s, int32_t mode);
  * row per thread), -1 (default) = automatic (transposed for n > 64, where it measures faster). Same arithmetic: results
  * are bit-identical (tests cross-check both). */
 int jrlqp_set_scan_transposed(jrlqp_solver * s, int32_t on);
+/* Bytes of ONE instance's G that cross the host link in jrlqp_solve_batch_host (non-shared G, no factor requested):
+ * the kernels read the lower triangle only, so the host entry point does not move all of G — with a pinned (page-locked,
+ * mapped) caller buffer and n <= 64 the kernels read G in place (lower triangle), otherwise G is uploaded as its left
+ * n/2 columns plus the bottom-right block. Environment overrides for tuning comparisons: JRLQP_G_ZEROCOPY=0|1,
+ * JRLQP_H2D_FULL_G=1. */
+int64_t jrlqp_host_g_bytes(const jrlqp_solver * s, int32_t pinned);
 /* Number of kernels this library has launched since it was loaded (all solvers). */
 int64_t jrlqp_launch_count(void);
 /* Last CUDA error string seen by this solver ("" if none). */

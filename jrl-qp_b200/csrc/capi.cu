@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +18,8 @@ using namespace jrlqp;
 namespace
 {
 
+static int g_zero_copy_G = -1; // kernels read G from the caller's pinned host buffer: 1 on, 0 off, -1 automatic (n <= 64); JRLQP_G_ZEROCOPY
+static bool g_h2d_lower = true; // host entry points upload only what the kernels read of G (see h2d_G)
 std::atomic<long long> g_launches{0};
 
 constexpr int kStreams = 3;
@@ -374,6 +377,8 @@ int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds,
     s->err = "this library contains sm_100a code only (Blackwell B200 required)";
     return JRLQP_ERR_CUDA;
   }
+  if(const char * e = getenv("JRLQP_G_ZEROCOPY")) g_zero_copy_G = e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1);
+  if(const char * e = getenv("JRLQP_H2D_FULL_G")) g_h2d_lower = !(e[0] == '1'); // tuning comparison: upload all of G
   s->num_sms = prop.multiProcessorCount;
   s->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   int rc = configure_kernel(s);
@@ -432,6 +437,15 @@ int jrlqp_set_kernel_path(jrlqp_solver * s, int32_t mode)
   s->wkernel = nullptr;
   cudaSetDevice(s->device);
   return configure_kernel(s);
+}
+
+int64_t jrlqp_host_g_bytes(const jrlqp_solver * s, int32_t pinned)
+{
+  if(!s) return 0;
+  const long long n = s->n, h = n / 2;
+  if(pinned && !s->large && (g_zero_copy_G == 1 || (g_zero_copy_G < 0 && n <= 64))) return 8 * (n * (n + 1) / 2); // lower triangle, read in place
+  if(g_h2d_lower && n >= 32) return 8 * (n * h + (n - h) * (n - h)); // left columns + bottom-right block
+  return 8 * n * n;
 }
 
 int jrlqp_set_scan_transposed(jrlqp_solver * s, int32_t on)
@@ -739,6 +753,28 @@ static cudaError_t h2d(double * dst, const double * src, long long stride, long 
   return cudaSuccess;
 }
 
+// Upload of G for the host entry points: the kernels read the lower triangle only (as the reference's LLT does,
+// src/GoldfarbIdnaniSolver.cpp:58), so the top-right (n/2) x (n - n/2) block of every instance need not cross PCIe:
+// the left n/2 columns go as one contiguous piece per instance (2-D copy), the bottom-right block as a 3-D copy
+// (rows of n - n/2 doubles). 25 % of G = 11.5 % of the input bytes of the headline shape. Falls back to the plain
+// copy when the layout is not the dense one or the blocks would be too small to be worth two descriptors.
+static cudaError_t h2d_G(double * dst, const double * src, long long stride, long long count, int n, int ld, cudaStream_t st)
+{
+  const int h = n / 2;
+  if(!g_h2d_lower || stride == 0 || count < 64 || ld != n || n < 32 || stride % n != 0) return h2d(dst, src, stride, count, n, n, ld, st);
+  cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)n * n, src, sizeof(double) * (size_t)stride, sizeof(double) * (size_t)h * n,
+                                    (size_t)count, cudaMemcpyHostToDevice, st);
+  if(e != cudaSuccess) return e;
+  cudaMemcpy3DParms p3{};
+  p3.srcPtr = make_cudaPitchedPtr(const_cast<double *>(src), sizeof(double) * (size_t)n, sizeof(double) * (size_t)n, (size_t)(stride / n));
+  p3.dstPtr = make_cudaPitchedPtr(dst, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n, (size_t)n);
+  p3.srcPos = make_cudaPos(sizeof(double) * (size_t)h, (size_t)h, 0);
+  p3.dstPos = make_cudaPos(sizeof(double) * (size_t)h, (size_t)h, 0);
+  p3.extent = make_cudaExtent(sizeof(double) * (size_t)(n - h), (size_t)(n - h), (size_t)count);
+  p3.kind = cudaMemcpyHostToDevice;
+  return cudaMemcpy3DAsync(&p3, st);
+}
+
 static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, bool warm)
 {
   int rc = validate(s, pb, res);
@@ -751,6 +787,20 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
 
   const long long B = pb->batch;
   const long long n = s->n, mc = s->mc, m = s->m;
+  // Where the host link bounds the call (small n: 43 KB of input per n = 50 QP against a solve of 0.5 us per QP and
+  // GPU), the kernels read G straight from the caller's PINNED buffer: only the lower triangle crosses PCIe, as
+  // SM-initiated reads concurrent with the DMA of the other arrays (measured, profiles/r01u_*: +5 % at n = 50, +9 % at
+  // n = 20 over the two-block upload, -5 % at n = 128, which is kernel-bound: automatic mode = n <= 64).
+  const bool zero_copy_G = !s->large && !res->L && pb->G_stride != 0 && (g_zero_copy_G == 1 || (g_zero_copy_G < 0 && s->n <= 64));
+  const double * g_dev_ptr_G = nullptr;
+  if(zero_copy_G)
+  {
+    cudaPointerAttributes at{};
+    if(cudaPointerGetAttributes(&at, pb->G) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
+      g_dev_ptr_G = static_cast<const double *>(at.devicePointer);
+    else
+      cudaGetLastError();
+  }
   // Pipeline: split the batch into chunks; chunk c runs H2D -> kernel -> D2H on stream c % kStreams,
   // so the copy engines and the SMs overlap across chunks.
   const long long per_qp_bytes = 8 * (n * n + n + mc * n + 2 * mc + 2 * s->nb);
@@ -810,8 +860,24 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
       dstride = blk;
       return h2d(d, h + b0 * hstride, hstride, cnt, rows, cols, ld, st);
     };
-    CK(up(s->d_G, pb->G, pb->G_stride, (int)n, (int)n, pb->ldg, dp.G, dp.G_stride));
-    dp.ldg = (int)n;
+    if(g_dev_ptr_G != nullptr)
+    {
+      // G is read by the kernels straight from the caller's pinned host buffer (lower triangle only: about half the
+      // bytes of G cross PCIe, as SM-initiated reads that overlap the DMA of the other arrays)
+      dp.G = g_dev_ptr_G + b0 * pb->G_stride;
+      dp.G_stride = pb->G_stride;
+    }
+    else if(pb->G_stride != 0 && !res->L)
+    {
+      // lower-triangle-only upload (the factor copy-out reads nothing of G's upper part either, but keep it simple)
+      double * d = s->d_G + b0 * n * n;
+      dp.G = d;
+      dp.G_stride = n * n;
+      CK(h2d_G(d, pb->G + b0 * pb->G_stride, pb->G_stride, cnt, (int)n, pb->ldg, st));
+    }
+    else
+      CK(up(s->d_G, pb->G, pb->G_stride, (int)n, (int)n, pb->ldg, dp.G, dp.G_stride));
+    dp.ldg = g_dev_ptr_G != nullptr ? pb->ldg : (int)n;
     CK(up(s->d_a, pb->a, pb->a_stride, (int)n, 1, (int)n, dp.a, dp.a_stride));
     if(mc)
     {

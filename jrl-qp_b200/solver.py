@@ -121,7 +121,7 @@ EXPORTED_SYMBOLS = [
     "jrlqp_structured_create", "jrlqp_structured_destroy", "jrlqp_structured_last_error",
     "jrlqp_structured_llt_device", "jrlqp_structured_llt_host", "jrlqp_structured_solve_device",
     "jrlqp_structured_solve_host", "jrlqp_structured_get_info", "jrlqp_selftest_arith",
-    "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host", "jrlqp_set_kernel_path", "jrlqp_set_scan_transposed",
+    "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host", "jrlqp_set_kernel_path", "jrlqp_set_scan_transposed", "jrlqp_host_g_bytes",
     "jrlqp_solve_sequence_device", "jrlqp_solve_sequence_host",
     "jrlqp_kkt_default_args", "jrlqp_kkt_check_device", "jrlqp_kkt_check_host",
     "jrlqp_blockgi_create", "jrlqp_blockgi_destroy", "jrlqp_blockgi_last_error", "jrlqp_blockgi_set_options",
@@ -156,6 +156,8 @@ def load_library():
         lib.jrlqp_set_stage_c.argtypes = [C.c_void_p, C.c_int32]
         lib.jrlqp_set_kernel_path.argtypes = [C.c_void_p, C.c_int32]
         lib.jrlqp_set_scan_transposed.argtypes = [C.c_void_p, C.c_int32]
+        lib.jrlqp_host_g_bytes.argtypes = [C.c_void_p, C.c_int32]
+        lib.jrlqp_host_g_bytes.restype = C.c_int64
         lib.jrlqp_solve_batch_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
         lib.jrlqp_solve_batch_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
         lib.jrlqp_solve_batch_warm_device.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result), C.c_void_p]
@@ -263,6 +265,10 @@ class BatchedGoldfarbIdnaniSolver:
         rc = self._lib.jrlqp_set_stage_c(self._h, int(mode))
         if rc != 0:
             raise JrlQpError(f"jrlqp_set_stage_c failed: {self._lib.jrlqp_last_error(self._h).decode()}")
+
+    def host_g_bytes(self, pinned=True):
+        """Bytes of one instance's G that cross the host link in solve() (jrlqp_host_g_bytes)."""
+        return int(self._lib.jrlqp_host_g_bytes(self._h, int(bool(pinned))))
 
     def set_scan_transposed(self, on):
         """Constraint scan of the non-staged shared-memory kernels: transposed copy of C (default) or C in place."""

@@ -203,6 +203,29 @@ def test_batch_of_one_and_empty_batch():
     assert sv.solve(pb0.G[:0], pb0.a[:0], pb0.C[:0], pb0.bl[:0], pb0.bu[:0], pb0.xl[:0], pb0.xu[:0]) == 0
 
 
+@pytest.mark.parametrize("ch,B", [(P.config_A(), 1500), (P.config_B(), 3000), (P.config_D(), 200)])
+def test_host_entry_moves_only_the_lower_triangle_of_G(ch, B):
+    """jrlqp_solve_batch_host: with a pinned caller buffer and n <= 64 the kernels read G in place over the host link;
+    otherwise G is uploaded as its left half plus the bottom-right block. The upper triangle is never read (as in the
+    reference, src/GoldfarbIdnaniSolver.cpp:58): poisoning it changes nothing."""
+    pb = P.random_problems(ch, B, seed=99)
+    ref = _oracle(pb)
+    n = pb.n
+    iu = np.triu_indices(n, 1)
+    Gp = torch.empty(pb.G.shape, dtype=torch.float64).pin_memory()
+    Gp.numpy()[:] = pb.G
+    Gp.numpy()[:, iu[1], iu[0]] = np.nan  # G [B][col][row]: entry (row < col) is the strict upper triangle
+    sv = S.BatchedGoldfarbIdnaniSolver(pb.n, pb.mc, True, B)
+    two_blocks = 8 * (n * (n // 2) + (n - n // 2) ** 2) if n >= 32 else 8 * n * n
+    assert sv.host_g_bytes(True) == (8 * n * (n + 1) // 2 if n <= 64 else two_blocks)
+    assert sv.host_g_bytes(False) == two_blocks
+    sv.solve(Gp.numpy(), pb.a, pb.C, pb.bl, pb.bu, pb.xl, pb.xu)  # pinned
+    assert_parity(sv.last, ref)
+    Gn = Gp.numpy().copy()  # pageable
+    sv.solve(Gn, pb.a, pb.C, pb.bl, pb.bu, pb.xl, pb.xu)
+    assert_parity(sv.last, ref)
+
+
 def test_shared_hessian_and_constraints_stride_zero():
     pb = P.random_problems(P.config_B(), 300, seed=31)
     rng = np.random.default_rng(0)
