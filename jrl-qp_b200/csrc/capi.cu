@@ -175,6 +175,9 @@ struct jrlqp_solver
   bool large = false;
   int lsmem_bytes[2] = {0, 0}, locc[2] = {0, 0}, lregs[2] = {0, 0}; // [cold, warm]
   double * d_work[2] = {nullptr, nullptr};
+  double * d_pre = nullptr; // factor of a batch-shared G (large-n kernel), see gi_params.h
+  int * d_pre_ok = nullptr;
+  int pre_smem = 0;
   int * d_busy[2] = {nullptr, nullptr};
   int work_slots[2] = {0, 0};
   long long work_stride[2] = {0, 0};
@@ -397,7 +400,7 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_ct, s->d_ct_busy, s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_pre, s->d_pre_ok, s->d_ct, s->d_ct_busy, s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -505,6 +508,40 @@ static int validate(const jrlqp_solver * s, const jrlqp_problem * pb, const jrlq
 
 static int configure_warm(jrlqp_solver * s);
 
+// Large-n kernel, G shared by the batch (stride 0): Cholesky and J = L^-T are computed ONCE, by one CTA running the
+// solver's own factorisation code (same bits), and every solver CTA copies them instead of redoing 2/3 n^3 flops per
+// instance (the MultiIK fixtures of config C spend ~100 % of a solve there). Asynchronous on `st`.
+static bool uses_prefactor(const jrlqp_solver * s, const jrlqp_problem * pb)
+{
+  return s->large && pb->G_stride == 0 && pb->batch >= 2;
+}
+
+static int prefactor(jrlqp_solver * s, const jrlqp_problem * pb, cudaStream_t st)
+{
+  const long long n = s->n, ldl = (n + 3) & ~3ll, nv = ldl;
+  if(!s->d_pre)
+  {
+    const LargeSmem lay(s->n, s->m, false);
+    s->pre_smem = lay.total * 8;
+    CK(cudaFuncSetAttribute(gi_large_prefactor_kernel<kLargeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->pre_smem));
+    CK(cudaMalloc(&s->d_pre, sizeof(double) * (size_t)(3 * n * ldl + 2 * nv)));
+    CK(cudaMalloc(&s->d_pre_ok, sizeof(int)));
+  }
+  GiParams p{};
+  p.n = s->n;
+  p.mc = s->mc;
+  p.nb = s->nb;
+  p.ldg = pb->ldg;
+  p.ldc = s->mc ? pb->ldc : s->n;
+  p.batch = 1;
+  p.G = pb->G;
+  p.sG = 0;
+  gi_large_prefactor_kernel<kLargeThreads><<<1, kLargeThreads, s->pre_smem, st>>>(p, s->d_pre, s->d_pre_ok);
+  g_launches.fetch_add(1);
+  CK(cudaGetLastError());
+  return JRLQP_OK;
+}
+
 // measured (profiles/r01m_*): the transposed scan pays for wide CTAs (n = 128: +6 %), not for n = 50 (-4 %)
 static bool scan_transposed_on(const jrlqp_solver * s)
 {
@@ -531,7 +568,8 @@ static int ensure_ct(jrlqp_solver * s)
   return JRLQP_OK;
 }
 
-static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter, bool warm = false, bool force_warm_start = false)
+static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, cudaStream_t st, unsigned long long * counter, bool warm = false, bool force_warm_start = false,
+                  bool pre_ready = false)
 {
   if(s->large)
   {
@@ -622,6 +660,16 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   const int occ = s->large ? s->locc[warm ? 1 : 0] : (warm ? s->wocc : s->occ);
   long long grid = std::min<long long>((long long)occ * s->num_sms, std::max<long long>(pb->batch, 1));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  if(uses_prefactor(s, pb))
+  {
+    if(!pre_ready)
+    {
+      int rc = prefactor(s, pb, st);
+      if(rc != JRLQP_OK) return rc;
+    }
+    p.pre = s->d_pre;
+    p.pre_ok = s->d_pre_ok;
+  }
   if(s->large)
   {
     p.work = s->d_work[warm ? 1 : 0];
@@ -830,6 +878,18 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
       CK(up1(s->d_xl, pb->xl, pb->xl_stride, (int)n, 1, (int)n));
       CK(up1(s->d_xu, pb->xu, pb->xu_stride, (int)n, 1, (int)n));
     }
+    if(s->large && pb->G_stride == 0 && B >= 2)
+    {
+      // factor of the shared G, once for the whole call (the chunks below re-use it)
+      jrlqp_problem pg{};
+      pg.batch = B;
+      pg.G = s->d_G;
+      pg.G_stride = 0;
+      pg.ldg = (int)n;
+      pg.ldc = (int)n;
+      int rcp = prefactor(s, &pg, s->streams[0]);
+      if(rcp != JRLQP_OK) return rcp;
+    }
     if(any)
     {
       if(!s->ev_shared) CK(cudaEventCreateWithFlags(&s->ev_shared, cudaEventDisableTiming));
@@ -913,7 +973,7 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
       dp.as_in = reinterpret_cast<const int8_t *>(das);
       dp.as_stride = pb->as_stride == 0 ? 0 : m;
     }
-    rc = launch(s, &dp, &dr, st, s->d_counters + (c % kMaxChunks), warm);
+    rc = launch(s, &dp, &dr, st, s->d_counters + (c % kMaxChunks), warm, false, /*pre_ready=*/s->large && pb->G_stride == 0 && B >= 2);
     if(rc != JRLQP_OK) return rc;
     CK(cudaMemcpyAsync(res->x + b0 * n, dr.x, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, st));
     if(res->u && m) CK(cudaMemcpyAsync(res->u + b0 * m, dr.u, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, st));
@@ -1009,7 +1069,7 @@ static int sequence_device_impl(jrlqp_solver * s, const jrlqp_problem * pb, cons
       p.as_in = res->active_set;
       p.as_stride = s->m;
     }
-    int rc = launch(s, &p, &r, st, counter, seq->warm != 0, seq->warm != 0);
+    int rc = launch(s, &p, &r, st, counter, seq->warm != 0, seq->warm != 0, /*pre_ready=*/t > 0);
     if(rc != JRLQP_OK) return rc;
     if(totals)
     {

@@ -223,7 +223,7 @@ struct GiLarge
   }
 
   // x = -G^-1 a by ONE warp (column-oriented forward / backward substitution, true division), f = a.x / 2
-  __device__ void initial_point(const double * __restrict__ ab)
+  __device__ void initial_point(const double * __restrict__ ab, const double * __restrict__ Lw)
   {
     for(int i = lane; i < n; i += 32) wv[i] = __ldg(ab + i);
     __syncwarp();
@@ -330,6 +330,41 @@ struct GiLarge
     sync();
   }
 
+  // ---- factor shared by the batch (P.pre, see gi_params.h)
+  __device__ __forceinline__ const double * pre_L() const { return P.pre + 2ll * n * ldl; }
+  // diag(L), 1 / diag(L) into shared memory, optional copy-out of L. False: G is not positive definite.
+  __device__ bool load_prefactor(long long b)
+  {
+    if(*P.pre_ok == 0) return false;
+    const int nv = (n + 3) & ~3;
+    const double * pd = P.pre + 3ll * n * ldl;
+    for(int i = tid; i < n; i += T)
+    {
+      ldiag[i] = pd[i];
+      rinv[i] = pd[nv + i];
+    }
+    if(P.L != nullptr)
+    {
+      const double * Lk = pre_L();
+      double * Lout = P.L + b * (long long)n * n;
+      for(int j = 0; j < n; ++j)
+        for(int i = j + tid; i < n; i += T) Lout[i + (long long)j * n] = Lk[i + (long long)j * ldl];
+    }
+    sync();
+    return true;
+  }
+  // Jc <- shared J (column-major, n x ldl), by the warps [w0, NW), 16-byte vectors
+  __device__ void copy_pre_J(int w0)
+  {
+    if(warp < w0) return;
+    const long long total2 = ((long long)n * ldl) >> 1; // ldl is a multiple of 4
+    const double2 * src = reinterpret_cast<const double2 *>(P.pre);
+    double2 * dst = reinterpret_cast<double2 *>(Jc);
+    const int nth = T - 32 * w0, t = tid - 32 * w0;
+#pragma unroll 8
+    for(long long e = t; e < total2; e += nth) dst[e] = __ldg(src + e);
+  }
+
   // init_ (src/GoldfarbIdnaniSolver.cpp:56-82)
   __device__ bool init(long long b)
   {
@@ -341,13 +376,28 @@ struct GiLarge
       const long long bytes = ((long long)(mc - 1) * P.ldc + n) * 8;
       for(long long o = (long long)tid * 128; o < bytes; o += (long long)T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg + o));
     }
-    if(!cholesky(b)) return false;
-    // warp 0: x = -G^-1 a (serial division chain) while the other warps build J
-    if(warp == 0) initial_point(ab);
-    build_J(1);
-    sync();
-    f = scr[1];
-    transpose_J(); // L is no longer needed: J moves into its storage, column-major
+    if(P.pre != nullptr)
+    {
+      // G is shared by the batch: its factor was computed once for the launch (gi_large_prefactor_kernel, same code,
+      // same bits). Warp 0 computes x = -G^-1 a from the shared L while the other warps copy J = L^-T.
+      if(!load_prefactor(b)) return false;
+      if(warp == 0)
+        initial_point(ab, pre_L());
+      else
+        copy_pre_J(1);
+      sync();
+      f = scr[1];
+    }
+    else
+    {
+      if(!cholesky(b)) return false;
+      // warp 0: x = -G^-1 a (serial division chain) while the other warps build J
+      if(warp == 0) initial_point(ab, Lw);
+      build_J(1);
+      sync();
+      f = scr[1];
+      transpose_J(); // L is no longer needed: J moves into its storage, column-major
+    }
     for(int c = tid; c < m; c += T)
     {
       stat[c] = ST_INACTIVE; // A_.reset()
@@ -981,6 +1031,35 @@ __global__ void __launch_bounds__(T, 2) gi_large_kernel(const GiParams p)
     __threadfence();
     atomicExch(p.work_busy + slot, 0);
   }
+}
+
+// Factor of a batch-shared G for the large-n kernel: ONE CTA runs the same Cholesky / J = L^-T code as the solver
+// CTAs (same bits) and leaves L, J (column-major), diag(L) and its reciprocals in `pre` (layout: gi_params.h).
+template<int T>
+__global__ void __launch_bounds__(T, 1) gi_large_prefactor_kernel(const GiParams p, double * pre, int * pre_ok)
+{
+  extern __shared__ __align__(16) double smem[];
+  GiLarge<T, false> cta(p, smem, pre); // p.L == nullptr, p.pre == nullptr (set by the host)
+  const int n = p.n, ldl = (n + 3) & ~3, nv = (n + 3) & ~3;
+  const bool ok = cta.cholesky(0);
+  if(!ok)
+  {
+    if(threadIdx.x == 0) *pre_ok = 0;
+    return;
+  }
+  double * Lk = pre + 2ll * n * ldl;
+  double * pd = pre + 3ll * n * ldl;
+  for(long long e = threadIdx.x; e < (long long)n * ldl; e += T) Lk[e] = cta.Lw[e];
+  for(int i = threadIdx.x; i < n; i += T)
+  {
+    pd[i] = cta.ldiag[i];
+    pd[nv + i] = cta.rinv[i];
+  }
+  __syncthreads();
+  cta.build_J(0);
+  __syncthreads();
+  cta.transpose_J();
+  if(threadIdx.x == 0) *pre_ok = 1;
 }
 
 } // namespace jrlqp

@@ -100,7 +100,7 @@ __device__ int warm_active_set(long long b)
 // accumulated by all the lanes in parallel (coalesced reads of L), then the 32 rows of the block are
 // finished one after the other, the new entry being broadcast to the lanes below it. Every chain still
 // receives its terms in ascending j: same bits as the sequential evaluation.
-__device__ void warm_B(long long b)
+__device__ void warm_B(long long b, const double * __restrict__ Lw)
 {
   for(int k = warp; k < q; k += NW)
   {
@@ -415,11 +415,22 @@ __device__ int init_warm(long long b, int & it)
   const double * __restrict__ ab = P.a + b * P.sa;
   int st = warm_active_set(b);
   if(st != TS_SUCCESS) return st;
-  if(!cholesky(b)) return TS_NON_POS_HESSIAN;
-  build_J(0);
-  warm_B(b); // reads L: before J takes over its storage
-  sync();
-  transpose_J();
+  if(P.pre != nullptr)
+  {
+    // factor shared by the batch (see init()): B = L^-1 N from the shared L, J copied
+    if(!load_prefactor(b)) return TS_NON_POS_HESSIAN;
+    copy_pre_J(0);
+    warm_B(b, pre_L());
+    sync();
+  }
+  else
+  {
+    if(!cholesky(b)) return TS_NON_POS_HESSIAN;
+    build_J(0);
+    warm_B(b, Lw); // reads L: before J takes over its storage
+    sync();
+    transpose_J();
+  }
   warm_qr();
   warm_JQ();
   for(int c = tid; c < m; c += T) eqf[c] = 0;

@@ -167,6 +167,50 @@ def test_multiik_simultaneous_cold_and_warm():
     assert np.allclose(gw["x"], g["x"], rtol=1e-6, atol=1e-8)
 
 
+def test_shared_G_is_factorised_once_and_matches_per_instance_factorisation():
+    """G shared by the batch (stride 0) on the global-workspace kernel: one CTA factorises it once (same code, same
+    bits) and the solver CTAs copy L^-T. Results must equal those of the same problems with G replicated per instance
+    (every CTA factorising its own copy), the oracle's, and the factor returned must be the same."""
+    torch = pytest.importorskip("torch")
+    pb = P.random_problems(P.config_A(), 300, seed=5)
+    rng = np.random.default_rng(1)
+    a = pb.a[0] + 0.05 * rng.standard_normal(pb.a.shape)
+    sh = P.ProblemBatch(pb.G[0], a, pb.C[0], pb.bl[0], pb.bu[0], pb.xl[0], pb.xu[0])
+    rep = P.ProblemBatch(np.repeat(pb.G[:1], 300, axis=0), a, np.repeat(pb.C[:1], 300, axis=0), np.repeat(pb.bl[:1], 300, axis=0),
+                         np.repeat(pb.bu[:1], 300, axis=0), np.repeat(pb.xl[:1], 300, axis=0), np.repeat(pb.xu[:1], 300, axis=0))
+    ref = _oracle(rep)
+    before = S.launch_count()
+    g_sh = _gpu(sh, want_L=True)  # host entry: prefactor once, chunks re-use it
+    assert S.launch_count() >= before + 2, "prefactor kernel + solver kernel"
+    g_rep = _gpu(rep, want_L=True)
+    assert_parity(g_sh, ref)
+    assert_parity(g_rep, ref)
+    assert np.array_equal(np.tril(g_sh["L"][7].T), np.tril(g_rep["L"][7].T))
+    # warm start from the cold active sets: zero iterations, same points
+    gw = _gpu_warm(sh, g_sh["active_set"])
+    assert_parity(gw, _oracle_warm(rep, g_sh["active_set"]))
+    assert (gw["iterations"] == 0).all()
+    # device entry point (one launch = one prefactor + one solver kernel) and a warm-started sequence (prefactor once)
+    sv = _solver(sh)
+    dev = torch.device("cuda:0")
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)  # noqa: E731
+    x = torch.empty((300, pb.n), dtype=torch.float64, device=dev)
+    it = torch.empty(300, dtype=torch.int32, device=dev)
+    sv.solve_device(300, t(sh.G), t(sh.a), t(sh.C), t(sh.bl), t(sh.bu), t(sh.xl), t(sh.xu), x, iterations=it,
+                    shared=("G", "C", "bl", "bu", "xl", "xu"))
+    torch.cuda.synchronize()
+    assert np.array_equal(x.cpu().numpy(), ref["x"]) and np.array_equal(it.cpu().numpy(), ref["iterations"])
+    a_seq = np.stack([a, a * 1.01, a * 0.99])
+    sv2 = _solver(sh, warm=True)
+    sv2.solve_sequence(sh.G, a_seq, sh.C, sh.bl, sh.bu, sh.xl, sh.xu, warm=True)
+    last = po.solve_batch(rep.G, a_seq[2], rep.C, rep.bl, rep.bu, rep.xl, rep.xu, nthreads=os.cpu_count())
+    assert np.allclose(sv2.last["x"], last["x"], rtol=1e-9, atol=1e-11) and (sv2.last["status_worst"] == 0).all()
+    # a shared G that is not positive definite: every instance reports NON_POS_HESSIAN
+    bad = P.ProblemBatch(-sh.G, a, sh.C, sh.bl, sh.bu, sh.xl, sh.xu)
+    gb = _gpu(bad)
+    assert (gb["status"] == S.TerminationStatus.NON_POS_HESSIAN).all()
+
+
 # ---------------------------------------------------------------------------------------------
 # warm start on the global-workspace kernel
 # ---------------------------------------------------------------------------------------------
