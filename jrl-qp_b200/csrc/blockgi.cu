@@ -4,6 +4,7 @@
 #include "structured_host.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,7 @@ struct jrlqp_blockgi
   unsigned char * d_out = nullptr;
   long long d_out_bytes = 0;
   cudaStream_t stream = nullptr;
+  int bthreads = 0; // threads per CTA of blockgi_kernel (the structured kernels keep s->g->threads)
   std::string err;
 
   bool check(cudaError_t e, const char * what)
@@ -68,8 +70,13 @@ int configure(jrlqp_blockgi * s)
     return JRLQP_ERR_ARG;
   }
   s->smem = (int)smem;
+  if(s->bthreads == 0)
+  {
+    s->bthreads = std::max(64, s->g->threads); // measured on config E (profiles/r01za_*): 32 -> 4.2 k, 64 -> 4.6 k, 128 -> 4.4 k, 256 -> 2.3 k QP/s
+    if(const char * e = getenv("JRLQP_BLOCKGI_THREADS")) s->bthreads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
+  }
   SCK(cudaFuncSetAttribute(blockgi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
-  SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ, blockgi_kernel, s->g->threads, s->smem));
+  SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ, blockgi_kernel, s->bthreads, s->smem));
   if(s->occ < 1)
   {
     s->err = "kernel cannot be made resident";
@@ -198,7 +205,7 @@ int jrlqp_blockgi_get_info(const jrlqp_blockgi * s, jrlqp_blockgi_info * info)
   info->n = s->n;
   info->mc = s->mc;
   info->nb = s->nb;
-  info->threads = s->g->threads;
+  info->threads = s->bthreads ? s->bthreads : s->g->threads;
   info->smem_bytes = s->smem;
   info->ctas_per_sm = s->occ;
   info->grid = s->grid;
@@ -291,7 +298,7 @@ int jrlqp_blockgi_solve_device(jrlqp_blockgi * s, const jrlqp_block_problem * pb
   p.batch = pb->batch;
   p.ticket = s->d_ticket;
   const long long grid = std::min<long long>(pb->batch, s->grid);
-  blockgi_kernel<<<(unsigned)grid, s->g->threads, s->smem, stream>>>(p);
+  blockgi_kernel<<<(unsigned)grid, s->bthreads, s->smem, stream>>>(p);
   count_launch();
   SCK(cudaGetLastError());
   return JRLQP_OK;
