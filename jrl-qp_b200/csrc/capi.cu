@@ -175,6 +175,8 @@ struct jrlqp_solver
   bool large = false;
   int lsmem_bytes[2] = {0, 0}, locc[2] = {0, 0}, lregs[2] = {0, 0}; // [cold, warm]
   double * d_work[2] = {nullptr, nullptr};
+  double * d_cts = nullptr; // transposed copy of a batch-shared C (large-n kernel)
+  int ldcts = 0;
   double * d_pre = nullptr; // factor of a batch-shared G (large-n kernel), see gi_params.h
   int * d_pre_ok = nullptr;
   int pre_smem = 0;
@@ -400,7 +402,7 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_pre, s->d_pre_ok, s->d_ct, s->d_ct_busy, s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_cts, s->d_pre, s->d_pre_ok, s->d_ct, s->d_ct_busy, s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -542,6 +544,26 @@ static int prefactor(jrlqp_solver * s, const jrlqp_problem * pb, cudaStream_t st
   return JRLQP_OK;
 }
 
+// Large-n kernel, C shared by the batch: one transposed copy per call for the coalesced constraint scan.
+static bool uses_shared_ct(const jrlqp_solver * s, const jrlqp_problem * pb)
+{
+  return s->large && s->mc > 0 && pb->C_stride == 0 && pb->batch >= 2 && s->scan_transposed != 0;
+}
+
+static int prepare_shared_ct(jrlqp_solver * s, const jrlqp_problem * pb, cudaStream_t st)
+{
+  if(!s->d_cts)
+  {
+    s->ldcts = (s->mc + 3) & ~3;
+    CK(cudaMalloc(&s->d_cts, sizeof(double) * (size_t)s->n * (size_t)s->ldcts));
+  }
+  const dim3 grid((unsigned)((s->mc + 31) / 32), (unsigned)((s->n + 31) / 32));
+  transpose_c_kernel<<<grid, 256, 0, st>>>(pb->C, pb->ldc, s->n, s->mc, s->d_cts, s->ldcts);
+  g_launches.fetch_add(1);
+  CK(cudaGetLastError());
+  return JRLQP_OK;
+}
+
 // measured (profiles/r01m_*): the transposed scan pays for wide CTAs (n = 128: +6 %), not for n = 50 (-4 %)
 static bool scan_transposed_on(const jrlqp_solver * s)
 {
@@ -669,6 +691,16 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
     }
     p.pre = s->d_pre;
     p.pre_ok = s->d_pre_ok;
+  }
+  if(uses_shared_ct(s, pb))
+  {
+    if(!pre_ready)
+    {
+      int rc = prepare_shared_ct(s, pb, st);
+      if(rc != JRLQP_OK) return rc;
+    }
+    p.ct = s->d_cts;
+    p.ldct = s->ldcts;
   }
   if(s->large)
   {
@@ -890,6 +922,16 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
       int rcp = prefactor(s, &pg, s->streams[0]);
       if(rcp != JRLQP_OK) return rcp;
     }
+    if(s->large && mc > 0 && pb->C_stride == 0 && B >= 2 && s->scan_transposed != 0)
+    {
+      jrlqp_problem pc{};
+      pc.batch = B;
+      pc.C = s->d_C;
+      pc.C_stride = 0;
+      pc.ldc = (int)n;
+      int rcc = prepare_shared_ct(s, &pc, s->streams[0]);
+      if(rcc != JRLQP_OK) return rcc;
+    }
     if(any)
     {
       if(!s->ev_shared) CK(cudaEventCreateWithFlags(&s->ev_shared, cudaEventDisableTiming));
@@ -973,7 +1015,7 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
       dp.as_in = reinterpret_cast<const int8_t *>(das);
       dp.as_stride = pb->as_stride == 0 ? 0 : m;
     }
-    rc = launch(s, &dp, &dr, st, s->d_counters + (c % kMaxChunks), warm, false, /*pre_ready=*/s->large && pb->G_stride == 0 && B >= 2);
+    rc = launch(s, &dp, &dr, st, s->d_counters + (c % kMaxChunks), warm, false, /*pre_ready=*/s->large); // shared factor / transposed C prepared above, once for all the chunks
     if(rc != JRLQP_OK) return rc;
     CK(cudaMemcpyAsync(res->x + b0 * n, dr.x, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, st));
     if(res->u && m) CK(cudaMemcpyAsync(res->u + b0 * m, dr.u, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, st));

@@ -382,9 +382,19 @@ struct GiLarge
       // same bits). Warp 0 computes x = -G^-1 a from the shared L while the other warps copy J = L^-T.
       if(!load_prefactor(b)) return false;
       if(warp == 0)
+      {
         initial_point(ab, pre_L());
+#ifdef JRLQP_DIAG_IP2
+        initial_point(ab, pre_L()); // DIAGNOSTIC: the cost of one more initial point
+#endif
+      }
       else
+      {
         copy_pre_J(1);
+#ifdef JRLQP_DIAG_CP2
+        copy_pre_J(1); // DIAGNOSTIC: the cost of one more copy of J
+#endif
+      }
       sync();
       f = scr[1];
     }
@@ -423,7 +433,10 @@ struct GiLarge
       if(__ballot_sync(JRLQP_FULL, act) == 0u) continue; // warp-uniform
       const double * ci = Cb + (long long)min(c, mc - 1) * ldC;
       const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0;
-      const double cx = cvec ? dot4_row<true, CH>(ci, xs, n) : dot4_row<false, CH>(ci, xs, n);
+      // C shared by the batch: scan its transposed copy (made once per call, coalesced across the constraints);
+      // lanes whose constraint is active issue no memory request
+      const double cx = P.ct != nullptr ? dot4_col<CH>(P.ct + min(c, mc - 1), P.ldct, xs, n, act)
+                                        : (cvec ? dot4_row<true, CH>(ci, xs, n, act) : dot4_row<false, CH>(ci, xs, n, act));
       if(act)
       {
         const double sl = cx - blc;
@@ -1030,6 +1043,26 @@ __global__ void __launch_bounds__(T, 2) gi_large_kernel(const GiParams p)
   {
     __threadfence();
     atomicExch(p.work_busy + slot, 0);
+  }
+}
+
+// Transposed copy of a batch-shared C (n x mc column-major, one normal per column) for the coalesced constraint scan of
+// the large-n kernel: Ct[k * ldct + c] = C[c * ldc + k], 32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose_c_kernel(const double * __restrict__ C, int ldc, int n, int mc, double * __restrict__ Ct, int ldct)
+{
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+  for(int r = ty; r < 32; r += 8)
+  {
+    const int c = c0 + r, k = k0 + tx;
+    tile[r][tx] = (c < mc && k < n) ? C[(long long)c * ldc + k] : 0.0;
+  }
+  __syncthreads();
+  for(int r = ty; r < 32; r += 8)
+  {
+    const int k = k0 + r, c = c0 + tx;
+    if(k < n && c < mc) Ct[(long long)k * ldct + c] = tile[tx][r];
   }
 }
 
