@@ -257,6 +257,126 @@ struct GiLarge
     if(lane == 0) scr[1] = fs;
   }
 
+  // x = -G^-1 a and f = a.x / 2 by the WHOLE CTA (used when the factor is shared by the batch and no other work can
+  // hide a serial warp): the two triangular solves run over 32-row diagonal blocks. The block itself is a serial
+  // chain on warp 0 (rows over the lanes, the block of L in the shared-memory tile, quotients from the stored
+  // reciprocals with their proof of correct rounding); the rows outside it are then updated by all the threads
+  // (one row per thread, 32 independent coalesced loads). Every element still receives its updates
+  // w_i = fma(-y_k, L(i,k), w_i) in ascending k (forward) / fma(-x_k, L(k,i), w_i) in descending k (backward), with a
+  // true division by the diagonal: the same operations as initial_point(), bit for bit.
+  __device__ void initial_point_blocked(const double * __restrict__ ab, const double * __restrict__ L)
+  {
+    for(int i = tid; i < n; i += T) wv[i] = __ldg(ab + i);
+    sync();
+    const int nblk = (n + 31) >> 5;
+#pragma unroll 1
+    for(int pass = 0; pass < 2; ++pass)
+    {
+#pragma unroll 1
+      for(int bi = 0; bi < nblk; ++bi)
+      {
+        const int r0 = 32 * (pass == 0 ? bi : nblk - 1 - bi);
+        const int nb = min(32, n - r0);
+        if(warp == 0)
+        {
+          // tile[jj * 33 + lane] = L(r0 + lane, r0 + jj), lower part of the diagonal block (coalesced along the rows)
+          const double * Lb = L + r0 + (long long)r0 * ldl;
+#pragma unroll 8
+          for(int jj = 0; jj < nb; ++jj) tile[jj * 33 + lane] = (lane < nb && lane >= jj) ? Lb[lane + (long long)jj * ldl] : 0.0;
+          __syncwarp();
+          const int rl = min(r0 + lane, n - 1);
+          double w = wv[rl];
+          const double ld = ldiag[rl], ri = rinv[rl];
+          if(pass == 0)
+          {
+#pragma unroll 1
+            for(int jj = 0; jj < nb; ++jj)
+            {
+              bool ok;
+              double cand = div_rcp(w, ld, ri, ok);
+              if(!ok && lane == jj) cand = w / ld; // only the lane whose entry is final matters
+              const double yk = __shfl_sync(JRLQP_FULL, cand, jj);
+              if(lane == jj)
+                w = yk;
+              else if(lane > jj)
+                w = fma(-yk, tile[jj * 33 + lane], w);
+            }
+          }
+          else
+          {
+#pragma unroll 1
+            for(int jj = nb - 1; jj >= 0; --jj)
+            {
+              bool ok;
+              double cand = div_rcp(w, ld, ri, ok);
+              if(!ok && lane == jj) cand = w / ld; // only the lane whose entry is final matters
+              const double xk = __shfl_sync(JRLQP_FULL, cand, jj);
+              if(lane == jj)
+                w = xk;
+              else if(lane < jj)
+                w = fma(-xk, tile[lane * 33 + jj], w); // L(r0 + jj, r0 + lane)
+            }
+          }
+          if(lane < nb) wv[r0 + lane] = w;
+        }
+        sync();
+        if(pass == 0)
+        {
+          // rows below the block: w_i -= sum_k y_k L(i, k), k ascending over the block
+          for(int i = r0 + nb + tid; i < n; i += T)
+          {
+            const double * Li = L + i + (long long)r0 * ldl;
+            double acc = wv[i];
+#pragma unroll 1
+            for(int j0 = 0; j0 < nb; j0 += 8)
+            {
+              double lv[8];
+#pragma unroll
+              for(int u = 0; u < 8; ++u) lv[u] = j0 + u < nb ? Li[(long long)(j0 + u) * ldl] : 0.0;
+#pragma unroll
+              for(int u = 0; u < 8; ++u)
+                if(j0 + u < nb) acc = fma(-wv[r0 + j0 + u], lv[u], acc);
+            }
+            wv[i] = acc;
+          }
+        }
+        else
+        {
+          // rows above the block: w_i -= sum_k x_k L(k, i), k descending over the block (32 contiguous entries of column i)
+          for(int i = tid; i < r0; i += T)
+          {
+            const double * Lc = L + r0 + (long long)i * ldl;
+            double acc = wv[i];
+#pragma unroll 1
+            for(int j0 = ((nb - 1) & ~7); j0 >= 0; j0 -= 8)
+            {
+              double lv[8];
+#pragma unroll
+              for(int u = 0; u < 8; ++u) lv[u] = j0 + u < nb ? Lc[j0 + u] : 0.0;
+#pragma unroll
+              for(int u = 7; u >= 0; --u)
+                if(j0 + u < nb) acc = fma(-wv[r0 + j0 + u], lv[u], acc);
+            }
+            wv[i] = acc;
+          }
+        }
+        sync();
+      }
+    }
+    if(warp == 0)
+    {
+      double facc = 0.0;
+      for(int i = lane; i < n; i += 32)
+      {
+        const double xi = -wv[i];
+        xs[i] = xi;
+        facc = fma(__ldg(ab + i), xi, facc); // dot32: lane = k & 31, ascending k
+      }
+      const double fs = 0.5 * warp_sum32(facc);
+      if(lane == 0) scr[1] = fs;
+    }
+  }
+
   // J = L^-T built row-major in Jr (upper triangle only; the strict lower triangle is never read),
   // thread = column j, by the warps [w0, NW): J(i,j) = (-dot4_{k=i+1..j}(L(k,i), J(k,j))) * (1 / L(i,i))
   __device__ void build_J(int w0)
@@ -379,22 +499,10 @@ struct GiLarge
     if(P.pre != nullptr)
     {
       // G is shared by the batch: its factor was computed once for the launch (gi_large_prefactor_kernel, same code,
-      // same bits). Warp 0 computes x = -G^-1 a from the shared L while the other warps copy J = L^-T.
+      // same bits). The CTA copies J = L^-T, then computes x = -G^-1 a from the shared L.
       if(!load_prefactor(b)) return false;
-      if(warp == 0)
-      {
-        initial_point(ab, pre_L());
-#ifdef JRLQP_DIAG_IP2
-        initial_point(ab, pre_L()); // DIAGNOSTIC: the cost of one more initial point
-#endif
-      }
-      else
-      {
-        copy_pre_J(1);
-#ifdef JRLQP_DIAG_CP2
-        copy_pre_J(1); // DIAGNOSTIC: the cost of one more copy of J
-#endif
-      }
+      copy_pre_J(0);
+      initial_point_blocked(ab, pre_L());
       sync();
       f = scr[1];
     }
