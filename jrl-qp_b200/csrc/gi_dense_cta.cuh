@@ -39,6 +39,9 @@ namespace jrlqp
 {
 
 #define JRLQP_FULL 0xffffffffu
+#ifndef JRLQP_MINB1
+#  define JRLQP_MINB1 16 // resident CTAs per SM the one-warp kernel is compiled for (register cap 65536 / (32 * MINB1))
+#endif
 
 // Optional per-phase cycle accounting (build with -DJRLQP_PHASE_TIMING; scripts/phase_timing.py):
 // every warp adds the cycles it spends in each phase — waits at barriers included — to
@@ -2261,7 +2264,7 @@ struct GiCta
 // Persistent kernel: grid = resident CTAs of the whole GPU; every CTA pulls the next problem index
 // from an atomic ticket counter, which absorbs the divergent iteration counts across QPs.
 template<int W, bool STAGE_C, bool WARM = false>
-__global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? 16 : (W == 2 ? 6 : 1)))) gi_dense_cta_kernel(const GiParams p)
+__global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W == 2 ? 6 : 1)))) gi_dense_cta_kernel(const GiParams p)
 {
   extern __shared__ __align__(16) double smem[];
   GiCta<W, STAGE_C, WARM> cta(p, smem);
