@@ -39,6 +39,9 @@ namespace jrlqp
 {
 
 #define JRLQP_FULL 0xffffffffu
+#ifndef JRLQP_OPT_V2_SCAN
+#  define JRLQP_OPT_V2_SCAN 0
+#endif
 #ifndef JRLQP_MINB1
 #  define JRLQP_MINB1 16 // resident CTAs per SM the one-warp kernel is compiled for (register cap 65536 / (32 * MINB1))
 #endif
@@ -175,7 +178,7 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
     {
-#if JRLQP_OPT_V2
+#if JRLQP_OPT_V2_SCAN // measured: -0.5 % at n = 50, -1.2 % at n = 20 (profiles/r01zf_*): off; the d = J^T n+ loop keeps its 128-bit loads
       // xs is 16-byte aligned and k + 4 u even: two 128-bit broadcast loads instead of four 64-bit ones
       const double2 x01 = *reinterpret_cast<const double2 *>(xs + k + 4 * u);
       const double2 x23 = *reinterpret_cast<const double2 *>(xs + k + 4 * u + 2);
