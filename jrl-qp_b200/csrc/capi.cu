@@ -554,11 +554,11 @@ static int prepare_shared_ct(jrlqp_solver * s, const jrlqp_problem * pb, cudaStr
 {
   if(!s->d_cts)
   {
-    s->ldcts = (s->mc + 3) & ~3;
-    CK(cudaMalloc(&s->d_cts, sizeof(double) * (size_t)s->n * (size_t)s->ldcts));
+    s->ldcts = JRLQP_CT_LD;
+    CK(cudaMalloc(&s->d_cts, sizeof(double) * (size_t)ct_doubles(s->n, s->mc)));
   }
   const dim3 grid((unsigned)((s->mc + 31) / 32), (unsigned)((s->n + 31) / 32));
-  transpose_c_kernel<<<grid, 256, 0, st>>>(pb->C, pb->ldc, s->n, s->mc, s->d_cts, s->ldcts);
+  transpose_c_kernel<<<grid, 256, 0, st>>>(pb->C, pb->ldc, s->n, s->mc, s->d_cts);
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return JRLQP_OK;
@@ -581,8 +581,8 @@ static int ensure_ct(jrlqp_solver * s)
   if(s->d_ct_busy) CK(cudaFree(s->d_ct_busy));
   s->d_ct = nullptr;
   s->d_ct_busy = nullptr;
-  s->ldct = (s->mc + 3) & ~3;
-  s->ct_stride = (((long long)s->n * s->ldct) + 15) & ~15ll;
+  s->ldct = JRLQP_CT_LD;
+  s->ct_stride = (ct_doubles(s->n, s->mc) + 15) & ~15ll;
   s->ct_slots = slots;
   CK(cudaMalloc(&s->d_ct_busy, sizeof(int) * (size_t)slots));
   CK(cudaMemset(s->d_ct_busy, 0, sizeof(int) * (size_t)slots));

@@ -236,9 +236,18 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
 // Ct[k * ld + c], global memory / L2): consecutive lanes = consecutive constraints read consecutive
 // addresses, so a warp-level load is two full cache lines instead of 32 sectors of 32 different rows.
 // L1 is bypassed (the slice is rewritten by this CTA for every problem).
+// The transposed copy is stored in groups of JRLQP_CT_LD = 128 constraints, element k of constraint c at
+// Ct[((c >> 7) * n + k) * 128 + (c & 127)]: the stride between consecutive k is a compile-time constant, so every
+// load of a chunk is one instruction with an immediate offset (a run-time leading dimension cost a 64-bit multiply
+// per load: 242 k of the 2.19 M warp-instructions of an n = 128 solve, profiles/r01zg_*).
+#define JRLQP_CT_LD 128
+__device__ __forceinline__ long long ct_offset(int c, int n) { return ((long long)(c >> 7) * n) * JRLQP_CT_LD + (c & (JRLQP_CT_LD - 1)); }
+__host__ __device__ inline long long ct_doubles(int n, int mc) { return (long long)((mc + JRLQP_CT_LD - 1) / JRLQP_CT_LD) * n * JRLQP_CT_LD; }
+
 template<int CH>
-__device__ __forceinline__ double dot4_col(const double * ci, const long long ld, const double * xs, int n, const bool act = true)
+__device__ __forceinline__ double dot4_col(const double * ci, const double * xs, int n, const bool act = true)
 {
+  constexpr int ld = JRLQP_CT_LD;
   double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   int k = 0;
 #pragma unroll 1
@@ -614,7 +623,6 @@ struct GiCta
     const double * __restrict__ Cg = P.C + b * P.sC;
     const int ldt = n | 1;
     const int chunk = max(1, (n * ldj) / ldt);
-    const long long ldct = P.ldct;
 #pragma unroll 1
     for(int c0 = 0; c0 < mc; c0 += chunk)
     {
@@ -629,9 +637,9 @@ struct GiCta
       for(int cc = tid; cc < cn; cc += T)
       {
         const double * src = Jb + cc * ldt;
-        double * dst = Ct + c0 + cc;
+        double * dst = Ct + ct_offset(c0 + cc, n);
 #pragma unroll 4
-        for(int k = 0; k < n; ++k) __stcg(dst + k * ldct, src[k]);
+        for(int k = 0; k < n; ++k) __stcg(dst + k * JRLQP_CT_LD, src[k]);
       }
       sync();
     }
@@ -1394,7 +1402,7 @@ struct GiCta
       const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
       double cx;
       if(!STAGE_C && Ct != nullptr)
-        cx = dot4_col<CH>(Ct + min(c, mc - 1), P.ldct, xs, n, JRLQP_OPT_PRED ? act : true);
+        cx = dot4_col<CH>(Ct + ct_offset(min(c, mc - 1), n), xs, n, JRLQP_OPT_PRED ? act : true);
       else
         cx = (!STAGE_C && cvec) ? dot4_row<true, CH>(ci, xs, n, JRLQP_OPT_PRED ? act : true) : dot4_row<false, CH>(ci, xs, n, JRLQP_OPT_PRED ? act : true);
       if(act)

@@ -543,7 +543,7 @@ struct GiLarge
       const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0;
       // C shared by the batch: scan its transposed copy (made once per call, coalesced across the constraints);
       // lanes whose constraint is active issue no memory request
-      const double cx = P.ct != nullptr ? dot4_col<CH>(P.ct + min(c, mc - 1), P.ldct, xs, n, act)
+      const double cx = P.ct != nullptr ? dot4_col<CH>(P.ct + ct_offset(min(c, mc - 1), n), xs, n, act)
                                         : (cvec ? dot4_row<true, CH>(ci, xs, n, act) : dot4_row<false, CH>(ci, xs, n, act));
       if(act)
       {
@@ -1155,8 +1155,8 @@ __global__ void __launch_bounds__(T, 2) gi_large_kernel(const GiParams p)
 }
 
 // Transposed copy of a batch-shared C (n x mc column-major, one normal per column) for the coalesced constraint scan of
-// the large-n kernel: Ct[k * ldct + c] = C[c * ldc + k], 32 x 32 tiles through shared memory.
-__global__ void __launch_bounds__(256) transpose_c_kernel(const double * __restrict__ C, int ldc, int n, int mc, double * __restrict__ Ct, int ldct)
+// the large-n kernel (layout: groups of 128 constraints, see ct_offset), 32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose_c_kernel(const double * __restrict__ C, int ldc, int n, int mc, double * __restrict__ Ct)
 {
   __shared__ double tile[32][33];
   const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
@@ -1170,7 +1170,7 @@ __global__ void __launch_bounds__(256) transpose_c_kernel(const double * __restr
   for(int r = ty; r < 32; r += 8)
   {
     const int k = k0 + r, c = c0 + tx;
-    if(k < n && c < mc) Ct[(long long)k * ldct + c] = tile[tx][r];
+    if(k < n && c < mc) Ct[ct_offset(c, n) + (long long)k * JRLQP_CT_LD] = tile[tx][r];
   }
 }
 

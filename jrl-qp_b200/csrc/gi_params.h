@@ -76,7 +76,8 @@ struct GiParams
   const double * pre;
   const int * pre_ok; // 1: G is positive definite
   // transposed copy of C for the coalesced constraint scan (gi_dense_cta.cuh, non-staged kernels): one slice of
-  // ct_stride doubles (n rows of ldct) per resident CTA, claimed like the work slices; null = scan C in place
+  // ct_stride doubles per resident CTA (groups of 128 constraints, layout: ct_offset in gi_dense_cta.cuh), claimed like the
+  // work slices; null = scan C in place. Large-n kernel: one copy of a batch-shared C for the whole launch (ct_slots == 0)
   double * ct;
   long long ct_stride;
   int * ct_busy;
