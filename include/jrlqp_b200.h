@@ -195,10 +195,11 @@ int jrlqp_set_stage_c(jrlqp_solver * s, int32_t mode);
  * 1 = shared-memory kernel (n <= 128), 2 = global-workspace kernel (any n <= 1024; used by the tests
  * to cross-check the two families on the same problems — their results are bit-identical). */
 int jrlqp_set_kernel_path(jrlqp_solver * s, int32_t mode);
-/* Constraint scan of the shared-memory kernels when C is not staged: 1 = every CTA keeps a transposed copy of its
- * problem's C in a global-memory slice (L2-resident) and scans it with coalesced loads, 0 = scan C in place (one strided
- * row per thread), -1 (default) = automatic (transposed for n > 64, where it measures faster). Same arithmetic: results
- * are bit-identical (tests cross-check both). */
+/* Constraint scan of the shared-memory kernels for n > 64 when C is not staged: 1 or -1 (default) = every CTA keeps a
+ * transposed copy of its problem's C in a global-memory slice (L2-resident) and scans it with coalesced loads (measures
+ * faster there), 0 = scan C in place (one strided row per thread). Same arithmetic: results are bit-identical (tests
+ * cross-check both). The kernels for n <= 64 always scan in place (the transposed scan measured slower there). Also
+ * selects whether the global-workspace kernel scans a transposed copy of a batch-shared C. */
 int jrlqp_set_scan_transposed(jrlqp_solver * s, int32_t on);
 /* Bytes of ONE instance's G that cross the host link in jrlqp_solve_batch_host (non-shared G, no factor requested):
  * the kernels read the lower triangle only, so the host entry point does not move all of G — with a pinned (page-locked,

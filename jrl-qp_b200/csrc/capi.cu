@@ -567,7 +567,7 @@ static int prepare_shared_ct(jrlqp_solver * s, const jrlqp_problem * pb, cudaStr
 // measured (profiles/r01m_*): the transposed scan pays for wide CTAs (n = 128: +6 %), not for n = 50 (-4 %)
 static bool scan_transposed_on(const jrlqp_solver * s)
 {
-  return s->scan_transposed == 1 || (s->scan_transposed < 0 && s->warps >= 3);
+  return s->scan_transposed != 0 && s->warps >= 3; // the narrow kernels (n <= 64) are compiled without it
 }
 
 // Slices for the transposed copy of C (gi_dense_cta.cuh: stage_ct): as many as CTAs of the shared-memory kernels

@@ -39,6 +39,15 @@ namespace jrlqp
 {
 
 #define JRLQP_FULL 0xffffffffu
+#ifndef JRLQP_CT_ALLW
+#  define JRLQP_CT_ALLW 0 // 1: compile the transposed-copy scan into the narrow kernels too (tuning comparison)
+#endif
+#ifndef JRLQP_OPT_PN
+#  define JRLQP_OPT_PN 1
+#endif
+#ifndef JRLQP_OPT_BSPLIT
+#  define JRLQP_OPT_BSPLIT 1
+#endif
 #ifndef JRLQP_OPT_V2_SCAN
 #  define JRLQP_OPT_V2_SCAN 0
 #endif
@@ -352,7 +361,11 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
 #pragma unroll 2
   for(; i >= q; --i)
   {
+#if JRLQP_OPT_PN
+    const double pn = ds[i - 1]; // operand of the next link (i == 0: ds[-1] is the padding of the vector stored before d; unused)
+#else
     const double pn = ds[max(i - 1, 0)]; // operand of the next link
+#endif
     // ---- fast path: t = p / rho, straight line
     const double e3 = fma(-rho, q0s, p);
     double a = fma(e3, rrE, q0s);
@@ -564,6 +577,9 @@ struct GiCta
   // ---- per-problem views
   const double *Cb, *bl, *bu, *xl, *xu;
   long long ldC; // leading dimension of the constraint-normal storage Cb (staged or global)
+  // The transposed-copy scan exists in the wide kernels only (n > 64, where it measures faster): in the narrow ones its
+  // code would sit, never executed, inside the hottest loop of an instruction-cache-sensitive kernel.
+  static constexpr bool CT_SCAN = !STAGE_C && (W >= 3 || JRLQP_CT_ALLW);
   bool cvec; // rows of Cb are 16-byte aligned (128-bit loads allowed)
   double * Ct = nullptr; // this CTA's slice for the transposed copy of C (null: scan C in place)
   bool ct_valid = false; // the slice holds the (batch-shared) C already
@@ -618,7 +634,7 @@ struct GiCta
   // coalesced (thread = constraint). Called before init() / init_warm().
   __device__ void stage_ct(long long b)
   {
-    if(STAGE_C || Ct == nullptr || mc == 0) return;
+    if(!CT_SCAN || Ct == nullptr || mc == 0) return;
     if(P.sC == 0 && ct_valid) return; // C shared by the batch: transposed once per CTA
     const double * __restrict__ Cg = P.C + b * P.sC;
     const int ldt = n | 1;
@@ -1401,10 +1417,18 @@ struct GiCta
       const double * ci = Cb + (long long)min(c, mc - 1) * ldC;
       const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
       double cx;
-      if(!STAGE_C && Ct != nullptr)
+      if(CT_SCAN && Ct != nullptr)
         cx = dot4_col<CH>(Ct + ct_offset(min(c, mc - 1), n), xs, n, JRLQP_OPT_PRED ? act : true);
       else
-        cx = (!STAGE_C && cvec) ? dot4_row<true, CH>(ci, xs, n, JRLQP_OPT_PRED ? act : true) : dot4_row<false, CH>(ci, xs, n, JRLQP_OPT_PRED ? act : true);
+      {
+        const bool pa = JRLQP_OPT_PRED ? act : true;
+        if(STAGE_C)
+          cx = dot4_row<false, CH>(ci, xs, n, pa); // shared memory, odd leading dimension
+        else if(cvec)
+          cx = dot4_row<true, CH>(ci, xs, n, pa);
+        else
+          cx = dot4_row<false, CH>(ci, xs, n, pa); // (as an out-of-line call: -2.3 % at n = 50, profiles/r01zk_ab_A.txt)
+      }
       if(act)
       {
         double sl = cx - blc;
@@ -1618,8 +1642,14 @@ struct GiCta
       }
       // (prefetching the operands of link k - 1 ahead of the dependent part of link k was measured twice — with a
       // rotating register set, -9 % at n = 50, and with two alternating sets, -6 %: profiles/r01n_ab_A.txt, r01o_ab_A.txt)
+      int k = q - 1;
+      // W >= 3: links k >= 32 touch the rows of every slot; links k < 32 only the rows of slot 0, and the pivot sits in
+      // slot 0: that loop carries one slot. Measured (profiles/r01zi_ab_*.txt): +4 % at n = 128, but -2.2 % at n = 50
+      // and -5.7 % at n = 20, where the second loop only adds code: compiled for the wide CTAs alone.
+      constexpr bool BSPLIT = JRLQP_OPT_BSPLIT && W >= 3;
+      const int klow = BSPLIT ? 32 : 0;
 #pragma unroll 1
-      for(int k = q - 1; k >= 0; --k)
+      for(; k >= klow; --k)
       {
         const double * Rk = Rp + colR(k);
         const double rkk = Rk[k], ri = rinv[k];
@@ -1646,6 +1676,30 @@ struct GiCta
           else if(r < k)
             w[s] = fma(-rk, col[s], w[s]);
         }
+      }
+      if(BSPLIT)
+      {
+#pragma unroll 1
+      for(; k >= 0; --k)
+      {
+        const double * Rk = Rp + colR(k);
+        const double rkk = Rk[k], ri = rinv[k];
+        const double col0 = Rk[min(lane, k)];
+        const double wk = __shfl_sync(JRLQP_FULL, w[0], k);
+        double rk;
+        if(pass == 0)
+        {
+          bool ok;
+          rk = div_rcp(wk, rkk, ri, ok);
+          allok = allok && ok;
+        }
+        else
+          rk = wk / rkk;
+        if(lane == k)
+          rr[0] = rk;
+        else if(lane < k)
+          w[0] = fma(-rk, col0, w[0]);
+      }
       }
     }
 #pragma unroll
@@ -2281,7 +2335,7 @@ __global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W
   GiCta<W, STAGE_C, WARM> cta(p, smem);
   unsigned long long * ticket = reinterpret_cast<unsigned long long *>(smem + p.off_scr + 12);
   int ct_slot = -1;
-  if(!STAGE_C && p.ct != nullptr && p.mc > 0)
+  if(!STAGE_C && (W >= 3 || JRLQP_CT_ALLW) && p.ct != nullptr && p.mc > 0)
   {
     // claim a slice for the transposed copy of C (as many slices as CTAs of these kernels can be resident)
     if(threadIdx.x == 0)
