@@ -224,6 +224,11 @@ def test_host_entry_moves_only_the_lower_triangle_of_G(ch, B):
     Gn = Gp.numpy().copy()  # pageable
     sv.solve(Gn, pb.a, pb.C, pb.bl, pb.bu, pb.xl, pb.xu)
     assert_parity(sv.last, ref)
+    if n <= 64:  # the warm-start entry point through the same in-place read of G
+        sv.options(S.SolverOptions().warmStart(True))
+        sv.solve(Gp.numpy(), pb.a, pb.C, pb.bl, pb.bu, pb.xl, pb.xu, experimental=True, as_in=ref["active_set"])
+        assert (sv.last["iterations"] == 0).all() and np.array_equal(sv.last["active_set"], ref["active_set"])
+        assert np.allclose(sv.last["x"], ref["x"], rtol=1e-6, atol=1e-8)
 
 
 def test_shared_hessian_and_constraints_stride_zero():
@@ -376,7 +381,10 @@ WARM_CHARACS = [  # tests/GoldfarbIdnaniSolverTest.cpp:139-143 (the reference's 
 ]
 
 
-@pytest.mark.parametrize("ch", WARM_CHARACS + [P.config_B(), P.config_A()], ids=lambda c: f"n{c.nVar}e{c.nEq}i{c.nIneq}b{int(c.bounds)}")
+WIDE = P.ProblemCharacteristics(70, 5, 150, nStrongActIneq=20, bounds=True, nStrongActBounds=5, doubleSidedIneq=True)  # W = 3, mc > 128
+
+
+@pytest.mark.parametrize("ch", WARM_CHARACS + [P.config_B(), P.config_A(), WIDE], ids=lambda c: f"n{c.nVar}e{c.nEq}i{c.nIneq}b{int(c.bounds)}")
 def test_warm_start_exact_guess_takes_zero_iterations(ch):
     """tests/GoldfarbIdnaniSolverTest.cpp:127-181: warm start from the active set of the cold solve gives
     SUCCESS, iterations() == 0, KKT, the planted solution; and the CUDA path equals the oracle bit for bit."""
@@ -396,7 +404,7 @@ def test_warm_start_exact_guess_takes_zero_iterations(ch):
         assert np.allclose(g[k], cold[k], rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("ch", WARM_CHARACS[2:] + [P.config_B()], ids=lambda c: f"n{c.nVar}e{c.nEq}i{c.nIneq}b{int(c.bounds)}")
+@pytest.mark.parametrize("ch", WARM_CHARACS[2:] + [P.config_B(), WIDE], ids=lambda c: f"n{c.nVar}e{c.nEq}i{c.nIneq}b{int(c.bounds)}")
 def test_warm_start_wrong_guesses(ch):
     """rubbish / partially wrong guesses (tests/GoldfarbIdnaniSolverTest.cpp:183-216): still SUCCESS + KKT,
     same trajectory as the oracle (drops of negative multipliers counted in iterations())."""
@@ -421,7 +429,7 @@ def test_warm_start_wrong_guesses(ch):
     assert ok.mean() > 0.9  # the reference itself notes that rubbish guesses can fail (its test disables that part)
     # the algorithm itself (reference included, see the FIXME at tests/GoldfarbIdnaniSolverTest.cpp:186) ends on a
     # non-optimal point for a few percent of such guesses; what is checked exactly is the parity above
-    assert P.test_kkt(g["x"], g["u"], pb)[ok].mean() > 0.95
+    assert P.test_kkt(g["x"], g["u"], pb)[ok].mean() > (0.95 if ch.nVar <= 50 else 0.9)  # 94.7 % at n = 70 (oracle and GPU alike)
 
 
 def test_experimental_cold_and_shared_guess():
