@@ -39,6 +39,12 @@ namespace jrlqp
 {
 
 #define JRLQP_FULL 0xffffffffu
+#ifndef JRLQP_UNR_CHOL
+#  define JRLQP_UNR_CHOL 2
+#endif
+#ifndef JRLQP_UNR_JB
+#  define JRLQP_UNR_JB 2
+#endif
 #ifndef JRLQP_CT_ALLW
 #  define JRLQP_CT_ALLW 0 // 1: compile the transposed-copy scan into the narrow kernels too (tuning comparison)
 #endif
@@ -560,6 +566,9 @@ struct GiCta
 #ifndef JRLQP_PF2
 #  define JRLQP_PF2 2
 #endif
+  // inner loops of the Cholesky and of J = L^-T: unrolled twice in the wide kernels (+2 % at n = 128; -0.5 % at n = 50 and
+  // -9 % at n = 20, profiles/r01zn_ab_*.txt)
+  static constexpr int UNR_CHOL = W >= 3 ? JRLQP_UNR_CHOL : 1, UNR_JB = W >= 3 ? JRLQP_UNR_JB : 1;
   static constexpr int UNR_DZ = JRLQP_UNR_DZ; // unroll factor of the d = J^T n+ and z = J2 d2 loops
   static constexpr int PF = W == 1 ? JRLQP_PF1 : (W == 2 ? JRLQP_PF2 : JRLQP_PF4); // rotations per chunk when the Givens table is applied
   // ---- immutable per-launch
@@ -707,7 +716,7 @@ struct GiCta
           const double * Lk = Jb + k * ldj;
           double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
           int j = 0;
-#pragma unroll 1
+#pragma unroll UNR_CHOL
           for(; j + 3 < k; j += 4)
           {
             a0 = fma(Li[j], Lk[j], a0);
@@ -820,7 +829,7 @@ struct GiCta
       for(int r = jmax - 1; r >= 0; --r)
       {
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 1
+#pragma unroll UNR_JB
         for(int k0 = r + 1; k0 <= jmax; k0 += 4)
         {
           // accumulator index (k - r - 1) & 3. Loads are unconditional (rows past j, even past n - 1,
