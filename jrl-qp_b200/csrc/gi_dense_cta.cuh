@@ -40,10 +40,10 @@ namespace jrlqp
 
 #define JRLQP_FULL 0xffffffffu
 #ifndef JRLQP_UNR_CHOL
-#  define JRLQP_UNR_CHOL 2
+#  define JRLQP_UNR_CHOL 4
 #endif
 #ifndef JRLQP_UNR_JB
-#  define JRLQP_UNR_JB 2
+#  define JRLQP_UNR_JB 4
 #endif
 #ifndef JRLQP_CT_ALLW
 #  define JRLQP_CT_ALLW 0 // 1: compile the transposed-copy scan into the narrow kernels too (tuning comparison)
@@ -566,10 +566,10 @@ struct GiCta
 #ifndef JRLQP_PF2
 #  define JRLQP_PF2 2
 #endif
-  // inner loops of the Cholesky and of J = L^-T: unrolled twice in the wide kernels (+2 % at n = 128; -0.5 % at n = 50 and
+  // inner loops of the Cholesky and of J = L^-T: unrolled four times in the wide kernels (+3 % at n = 128; -0.5 % at n = 50 and
   // -9 % at n = 20, profiles/r01zn_ab_*.txt)
   static constexpr int UNR_CHOL = W >= 3 ? JRLQP_UNR_CHOL : 1, UNR_JB = W >= 3 ? JRLQP_UNR_JB : 1;
-  static constexpr int UNR_DZ = JRLQP_UNR_DZ; // unroll factor of the d = J^T n+ and z = J2 d2 loops
+  static constexpr int UNR_DZ = W >= 3 ? 4 : JRLQP_UNR_DZ; // unroll factor of the d = J^T n+ and z = J2 d2 loops
   static constexpr int PF = W == 1 ? JRLQP_PF1 : (W == 2 ? JRLQP_PF2 : JRLQP_PF4); // rotations per chunk when the Givens table is applied
   // ---- immutable per-launch
   const GiParams & P;
