@@ -65,7 +65,7 @@ struct Layout
 {
   int ldj, ldcs, npad;
   int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_rinv, off_scr, off_C;
-  int off_alist, off_gk, off_iscr, off_stat, off_eq;
+  int off_alist, off_gk, off_iscr, off_stat, off_eq, off_il;
   int off_V, off_bact, off_hco, off_alpha;
   int total_doubles;
 };
@@ -118,6 +118,8 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage, bool warm = fal
   o += (mc + nb + 7) / 8 + 1;
   L.off_eq = o;
   o += (mc + nb + 7) / 8 + 1;
+  L.off_il = o; // uint16 per general constraint
+  o += (mc + 3) / 4;
   L.off_V = L.off_bact = L.off_hco = L.off_alpha = o;
   if(warm)
   {
@@ -675,6 +677,7 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.off_iscr = lay.off_iscr;
   p.off_stat = lay.off_stat;
   p.off_eq = lay.off_eq;
+  p.off_il = lay.off_il;
   p.off_V = lay.off_V;
   p.off_bact = lay.off_bact;
   p.off_hco = lay.off_hco;

@@ -303,8 +303,9 @@ __device__ __forceinline__ double dot4_col(const double * ci, const double * xs,
 // Free function (one warp, lane = threadIdx.x & 31) shared by the shared-memory kernel and the
 // global-workspace kernel (gi_large.cuh).
 // (c, s) of rotation i from what the recurrence stashed: (t, u) and the branch taken in makeGivens
-__device__ __forceinline__ double2 givens_cs(const int kind, const double a, const double u)
+__device__ __forceinline__ double2 givens_cs(const int kind8, const double a, const double u)
 {
+  const int kind = kind8 & 7; // bit 3: "quotient proven after the loop" (givens_chain)
   double c, sn;
   if(kind == 0)
   {
@@ -336,18 +337,21 @@ __device__ __forceinline__ double2 givens_cs(const int kind, const double a, con
 
 // SPLIT: the lane-parallel parts on either side of the recurrence (the reciprocals 1 / d[i] before it, the
 // (c, s) pairs after it) are done by the caller with all the threads of the CTA, off this warp's critical path.
+// gr: n doubles of scratch (the incoming rho of every link, for the deferred proof).
 template<bool SPLIT = false>
-__device__ __forceinline__ void givens_chain(const int q, const int n, const int lane, const double * ds, double2 * gcs, double * gc, double * gs, int * gk, double * scr)
+__device__ __forceinline__ void givens_chain(const int q, const int n, const int lane, const double * ds, double2 * gcs, double * gc, double * gs, int * gk, double * scr, double * gr)
 {
   // Latency of one link is what matters here. Per link, Eigen's makeGivens needs t = num / den,
   // u = sqrt(1 + t^2), r = den u, with den = rho (the running value) in the common case
   // |rho| >= |p|. The stock division and square root chain ~20 dependent FP64 operations; here
   //  * a reciprocal of rho is carried along the recurrence (rr0 = |1/rho| * y1, y1 ~ 1/sqrt(1+t^2)
   //    being a by-product of the square root), so that t costs 2 dependent FMAs after rho is known
-  //    (div_rcp with the product q0 = p * rr0 issued one link ahead), and is PROVEN to be the
-  //    correctly rounded quotient by an exact remainder test off the chain (see fp64_exact.cuh);
-  //  * every other case (|d[i]| > |rho|, a zero operand, proof declined) leaves the straight-line
-  //    fast path through one branch and is evaluated with precomputed 1 / d[i] or literally.
+  //    (div_rcp with the product q0 = p * rr0 issued one link ahead);
+  //  * that quotient is PROVEN to be the correctly rounded one by an exact remainder test (see fp64_exact.cuh) which
+  //    is not evaluated in the loop: the loop stashes (t, rho) per link and, afterwards, every lane checks one link.
+  //    If a proof is declined (rare) the chain is redone with every quotient taken literally;
+  //  * every other case (|d[i]| > |rho|, a zero operand) leaves the straight-line fast path through one branch and
+  //    is evaluated with precomputed 1 / d[i] or literally.
   double * rpv = reinterpret_cast<double *>(gcs); // 1 / d[i]; gcs is only written after the chain
   if(!SPLIT)
   {
@@ -358,93 +362,114 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
     }
     __syncwarp();
   }
-  double rho = ds[n - 1];
-  double rrR = rpv[n - 1]; // reciprocal of rho, refined
-  double rrE = rrR; // reciprocal of rho available before rho itself (feeds q0 and the correction)
-  int i = n - 2;
-  double p = ds[max(i, 0)];
-  double q0s = p * rrE; // first product of the quotient p / rho, issued ahead
-#pragma unroll 2
-  for(; i >= q; --i)
+  bool careful = false;
+#pragma unroll 1
+  for(;;)
   {
-#if JRLQP_OPT_PN
-    const double pn = ds[i - 1]; // operand of the next link (i == 0: ds[-1] is the padding of the vector stored before d; unused)
-#else
-    const double pn = ds[max(i - 1, 0)]; // operand of the next link
-#endif
-    // ---- fast path: t = p / rho, straight line
-    const double e3 = fma(-rho, q0s, p);
-    double a = fma(e3, rrE, q0s);
-    const double e2 = fma(-rho, a, p); // exact remainder (proof)
-    double y1;
-    const double us = sqrt_rsqrt(fma(a, a, 1.0), y1);
-    double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
-    double rr0 = fabs(rrR) * y1; // ~ 1 / r, known before r
-    double rrn = fma(rr0, fma(-r, rr0, 1.0), rr0);
-    double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
-    int kind = 3;
-    // proof that a == RN(p / rho): |e2| < |rho| ulp(a) / 2, a not a power of two, nothing near underflow
-    const int ahi = __double2hiint(a);
-    const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
-    const double tol = fabs(rho) * hu;
-    const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
-#ifdef JRLQP_DIAG_NOPROOF
-    const bool fast = fabs(p) <= fabs(rho) && p != 0.0; // DIAGNOSTIC ONLY (not exact): cost of the proof on the chain
-#else
-    const bool fast = fabs(e2) < tol && tol > 1e-270 && !pow2 && fabs(p) <= fabs(rho) && p != 0.0;
-#endif
-    if(!fast)
+    double rho = ds[n - 1];
+    double rrR = rpv[n - 1]; // reciprocal of rho, refined
+    double rrE = rrR; // reciprocal of rho available before rho itself (feeds q0 and the correction)
+    int i = n - 2;
+    double p = ds[max(i, 0)];
+    double q0s = p * rrE; // first product of the quotient p / rho, issued ahead
+#pragma unroll 2
+    for(; i >= q; --i)
     {
-      const double rp = rpv[i];
-      if(rho == 0.0)
+#if JRLQP_OPT_PN
+      const double pn = ds[i - 1]; // operand of the next link (i == 0: ds[-1] is the padding of the vector stored before d; unused)
+#else
+      const double pn = ds[max(i - 1, 0)]; // operand of the next link
+#endif
+      // ---- fast path: t = p / rho, straight line
+      const double e3 = fma(-rho, q0s, p);
+      double a = fma(e3, rrE, q0s);
+      double y1;
+      const double us = sqrt_rsqrt(fma(a, a, 1.0), y1);
+      double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
+      double rr0 = fabs(rrR) * y1; // ~ 1 / r, known before r
+      double rrn = fma(rr0, fma(-r, rr0, 1.0), rr0);
+      double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
+      int kind = 3 | 8; // bit 3: the quotient of this link is to be proven after the loop
+      const bool fast = !careful && fabs(p) <= fabs(rho) && p != 0.0;
+      if(!fast)
       {
-        kind = 0;
-        a = p;
-        u = 1.0;
-        r = fabs(p);
-        rr0 = fabs(rp);
+        const double rp = rpv[i];
+        if(rho == 0.0)
+        {
+          kind = 0;
+          a = p;
+          u = 1.0;
+          r = fabs(p);
+          rr0 = fabs(rp);
+        }
+        else if(p == 0.0)
+        {
+          kind = 1;
+          a = rho;
+          u = 1.0;
+          r = fabs(rho);
+          rr0 = fabs(rrR);
+        }
+        else
+        {
+          const bool pg = fabs(p) > fabs(rho);
+          kind = pg ? 2 : 3;
+          const double num = pg ? rho : p, den = pg ? p : rho;
+          bool ok = false;
+          if(pg) a = div_rcp(num, den, rp, ok); // 1 / p was precomputed
+          if(!ok) a = num / den;
+          const double uu = sqrt(fma(a, a, 1.0));
+          u = den < 0.0 ? -uu : uu;
+          r = den * u;
+          rr0 = 1.0 / r;
+        }
+        rrn = rr0;
       }
-      else if(p == 0.0)
+      if(lane == 0)
       {
-        kind = 1;
-        a = rho;
-        u = 1.0;
-        r = fabs(rho);
-        rr0 = fabs(rrR);
+        // stash (t, u), the branch taken and the divisor of the quotient to be proven
+        gc[i] = a;
+        gs[i] = u;
+        gk[i] = kind;
+        gr[i] = rho;
       }
-      else
-      {
-        const bool pg = fabs(p) > fabs(rho);
-        kind = pg ? 2 : 3;
-        const double num = pg ? rho : p, den = pg ? p : rho;
-        bool ok = false;
-        if(pg) a = div_rcp(num, den, rp, ok); // 1 / p was precomputed
-        if(!ok) a = num / den;
-        const double uu = sqrt(fma(a, a, 1.0));
-        u = den < 0.0 ? -uu : uu;
-        r = den * u;
-        rr0 = 1.0 / r;
-      }
-      rrn = rr0;
+      rho = r;
+      rrR = rrn;
+      rrE = rr0;
+      p = pn;
+      q0s = pn * rr0;
     }
     if(lane == 0)
     {
-      // stash (t, u) and what the trivial branches need
-      gc[i] = a;
-      gs[i] = u;
-      gk[i] = kind;
+      scr[11] = rrR; // ~ 1 / rho: reciprocal of the new diagonal entry of R
+      scr[10] = rho;
     }
-    rho = r;
-    rrR = rrn;
-    rrE = rr0;
-    p = pn;
-    q0s = pn * rr0;
+    __syncwarp();
+    if(careful) break;
+    // ---- deferred proofs, one link per lane: t == RN(p / rho) iff |p - rho t| < |rho| ulp(t) / 2, t not a power of
+    //      two, nothing near underflow
+    bool ok = true;
+#pragma unroll 1
+    for(int j = q + lane; j <= n - 2; j += 32)
+    {
+      if(gk[j] & 8)
+      {
+        const double a = gc[j], rh = gr[j];
+        const double e2 = fma(-rh, a, ds[j]); // exact remainder
+        const int ahi = __double2hiint(a);
+        const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
+        const double tol = fabs(rh) * hu;
+        const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
+#ifndef JRLQP_DIAG_NOPROOF
+        ok = ok && fabs(e2) < tol && tol > 1e-270 && !pow2;
+#endif
+      }
+    }
+    if(__all_sync(JRLQP_FULL, ok)) break;
+    careful = true;
   }
-  if(lane == 0) scr[11] = rrR; // ~ 1 / rho: reciprocal of the new diagonal entry of R
-  if(lane == 0) scr[10] = rho;
   if(!SPLIT)
   {
-    __syncwarp();
 #pragma unroll 1
     for(int i = q + lane; i <= n - 2; i += 32)
     {
@@ -580,6 +605,7 @@ struct GiCta
   int * alist;
   int * gk;
   int * iscr;
+  unsigned short * ilist; // compacted list of the inactive general constraints (constraint scan)
   signed char * stat;
   double *Vp, *bact, *hco, *alp; // warm start: Householder vectors (packed), b_act, tau, alpha = J^T a
   signed char * eqf; // 1 where bl == bu (resp. xl == xu): constraints initActiveSet pre-activates
@@ -622,6 +648,7 @@ struct GiCta
     iscr = reinterpret_cast<int *>(smem + p.off_iscr);
     stat = reinterpret_cast<signed char *>(smem + p.off_stat);
     eqf = reinterpret_cast<signed char *>(smem + p.off_eq);
+    ilist = reinterpret_cast<unsigned short *>(smem + p.off_il);
     Vp = smem + p.off_V;
     bact = smem + p.off_bact;
     hco = smem + p.off_hco;
@@ -1397,74 +1424,168 @@ struct GiCta
   }
 
   // ------------------------------------------------------------------------------------------
-  // selectViolatedConstraint_ (src/GoldfarbIdnaniSolver.cpp:84-134), thread = constraint.
-  // Also returns the selected constraint's cx so that computeStepLength_ can reuse it (x is
-  // unchanged between the two when step 1 was executed; same dot4 => same bits).
+  // selectViolatedConstraint_ (src/GoldfarbIdnaniSolver.cpp:84-134).
+  //
+  // The scan is run by NSW "scan warps" (scan_partial), each leaving its first-minimum candidate in shared memory;
+  // every thread then combines the NSW candidates after the next block barrier (scan_combine). Splitting it this way
+  // lets the scan of the NEXT iteration run on warps that are otherwise parked while warp 0 does the back
+  // substitution (solve()): it reads a speculative x (x + t2 z, the point of a full step) and is simply discarded
+  // when the step turns out to be partial.
+  //
+  // Row scan (C in place / staged): the inactive constraints are first compacted into `ilist` (ballot + popc, every
+  // scan warp builds the same list), then TWO lanes share one constraint: lane h = 0 owns the dot4 accumulators 0 and
+  // 1 (elements k = 4j, 4j+1), lane h = 1 the accumulators 2 and 3 (k = 4j+2, 4j+3). Each accumulator is still the
+  // canonical chain (k ascending), the result (a0 + a1) + (a2 + a3) is formed by one shuffle, so the bits are those of
+  // dot4. A warp-level load then touches 16 rows x 32 contiguous bytes (whole sectors, nothing fetched twice), all the
+  // loads of a row are in flight together (one L2 round trip per round instead of one per chunk), and a round covers
+  // 16 NSW inactive constraints — the active ones (60 % at the optimum of config A) cost nothing.
   // ------------------------------------------------------------------------------------------
-  // TW = number of warps taking part (W: whole CTA, barriers allowed).
-#ifndef JRLQP_SELECT_INLINE
-#  define JRLQP_SELECT_INLINE 1
-#endif
-  template<int TW>
-#if JRLQP_SELECT_INLINE
-  __device__ __forceinline__ Sel select(double & cx_sel)
-#else
-  __device__ __noinline__ Sel select(double & cx_sel)
-#endif
+  static constexpr int NJ = 8 * W; // chunks of 4 elements per row: n <= 32 W
+
+  template<bool VEC>
+  __device__ __forceinline__ double half_dot(const double * ci, const double * xh, const int rem, const int nj, const bool act) const
   {
-    constexpr int TT = 32 * TW;
-    const int tt = TW == 1 ? lane : tid;
+    // ci, xh already point at element 2h; this lane owns the elements k' = 4j, 4j+1 < rem of that view.
+    // The padding of the x vector (up to npad) is kept at zero, and a missing element is loaded as zero:
+    // fma(0, 0, acc) == acc exactly (acc is never -0), so the unconditional FMAs below do not change any bit.
+    double2 v[NJ];
+#pragma unroll
+    for(int j = 0; j < NJ; ++j)
+    {
+      v[j] = make_double2(0.0, 0.0);
+      if(j < nj && act)
+      {
+        if(VEC)
+        {
+          if(4 * j + 1 < rem)
+            v[j] = *reinterpret_cast<const double2 *>(ci + 4 * j);
+          else if(4 * j < rem)
+            v[j].x = ci[4 * j];
+        }
+        else
+        {
+          if(4 * j < rem) v[j].x = ci[4 * j];
+          if(4 * j + 1 < rem) v[j].y = ci[4 * j + 1];
+        }
+      }
+    }
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for(int j = 0; j < NJ; ++j)
+    {
+      if(j < nj)
+      {
+        const double2 x2 = *reinterpret_cast<const double2 *>(xh + 4 * j);
+        a0 = fma(v[j].x, x2.x, a0);
+        a1 = fma(v[j].y, x2.y, a1);
+      }
+    }
+    return a0 + a1;
+  }
+
+  // One scan warp's share. xv: the point to test (16-byte aligned, zero padding); excl: a constraint to be treated as
+  // active whatever its status says (the one being added by the step in flight; -1: none); sw: index of this warp
+  // among the NSW scan warps.
+  template<int NSW>
+  __device__ __forceinline__ void scan_partial(const double * xv, const int excl, const int sw)
+  {
+    constexpr int TT = 32 * NSW;
+    const int tt = 32 * sw + lane;
     double best = 0.0;
     double bestcx = 0.0;
     int code = JRLQP_NONE;
     bool bothneg = false;
-    for(int base = 0; base < mc; base += TT)
+    if(CT_SCAN && Ct != nullptr)
     {
-      int c = base + tt;
-      bool act = c < mc && stat[c] == ST_INACTIVE;
-      if(__ballot_sync(JRLQP_FULL, act) == 0u) continue; // warp-uniform
-      const double * ci = Cb + (long long)min(c, mc - 1) * ldC;
-      const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
-      double cx;
-      if(CT_SCAN && Ct != nullptr)
-        cx = dot4_col<CH>(Ct + ct_offset(min(c, mc - 1), n), xs, n, JRLQP_OPT_PRED ? act : true);
-      else
+      // wide kernels: thread = constraint over the transposed copy of C (coalesced along the constraints)
+      for(int base = 0; base < mc; base += TT)
       {
-        const bool pa = JRLQP_OPT_PRED ? act : true;
-        if(STAGE_C)
-          cx = dot4_row<false, CH>(ci, xs, n, pa); // shared memory, odd leading dimension
-        else if(cvec)
-          cx = dot4_row<true, CH>(ci, xs, n, pa);
-        else
-          cx = dot4_row<false, CH>(ci, xs, n, pa); // (as an out-of-line call: -2.3 % at n = 50, profiles/r01zk_ab_A.txt)
-      }
-      if(act)
-      {
-        double sl = cx - blc;
-        double su = buc - cx;
-        if(sl < 0.0 && su < 0.0) bothneg = true;
-        if(sl < best)
+        const int c = base + tt;
+        const bool act = c < mc && stat[c] == ST_INACTIVE && c != excl;
+        if(__ballot_sync(JRLQP_FULL, act) == 0u) continue; // warp-uniform
+        const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
+        const double cx = dot4_col<CH>(Ct + ct_offset(min(c, mc - 1), n), xv, n, act);
+        if(act)
         {
-          best = sl;
-          bestcx = cx;
-          code = c * 8 + ST_LOWER;
+          const double sl = cx - blc;
+          const double su = buc - cx;
+          if(sl < 0.0 && su < 0.0) bothneg = true;
+          if(sl < best)
+          {
+            best = sl;
+            bestcx = cx;
+            code = c * 8 + ST_LOWER;
+          }
+          else if(su < best)
+          {
+            best = su;
+            bestcx = cx;
+            code = c * 8 + ST_UPPER;
+          }
         }
-        else if(su < best)
+      }
+    }
+    else if(mc > 0)
+    {
+      // (1) compact list of the inactive constraints
+      int ni = 0;
+      for(int base = 0; base < mc; base += 32)
+      {
+        const int c = base + lane;
+        const bool in = c < mc && stat[c] == ST_INACTIVE && c != excl;
+        const unsigned msk = __ballot_sync(JRLQP_FULL, in);
+        if(in) ilist[ni + __popc(msk & ((1u << lane) - 1u))] = (unsigned short)c;
+        ni += __popc(msk);
+      }
+      __syncwarp();
+      // (2) rounds of TT / 2 constraints, two lanes per constraint
+      const int h = lane & 1;
+      const int nj = (n + 3) >> 2;
+      const int rem = n - 2 * h;
+      const double * xh = xv + 2 * h;
+#pragma unroll 1
+      for(int base = 0; base < ni; base += TT / 2)
+      {
+        const int idx = base + (tt >> 1);
+        const bool act = idx < ni;
+        const int c = act ? (int)ilist[idx] : 0;
+        const double * ci = Cb + (long long)c * ldC + 2 * h;
+        const double blc = act ? bl[c] : 0.0, buc = act ? bu[c] : 0.0; // issued ahead of the dot product
+        double s01;
+        if(!STAGE_C && cvec)
+          s01 = half_dot<true>(ci, xh, rem, nj, act);
+        else
+          s01 = half_dot<false>(ci, xh, rem, nj, act);
+        const double s23 = __shfl_xor_sync(JRLQP_FULL, s01, 1);
+        const double cx = h == 0 ? s01 + s23 : s23 + s01; // (a0 + a1) + (a2 + a3) on both lanes
+        if(act)
         {
-          best = su;
-          bestcx = cx;
-          code = c * 8 + ST_UPPER;
+          const double sl = cx - blc;
+          const double su = buc - cx;
+          if(sl < 0.0 && su < 0.0) bothneg = true;
+          if(sl < best)
+          {
+            best = sl;
+            bestcx = cx;
+            code = c * 8 + ST_LOWER;
+          }
+          else if(su < best)
+          {
+            best = su;
+            bestcx = cx;
+            code = c * 8 + ST_UPPER;
+          }
         }
       }
     }
     for(int base = 0; base < nb; base += TT)
     {
-      int c = base + tt;
-      if(c < nb && stat[mc + c] == ST_INACTIVE)
+      const int c = base + tt;
+      if(c < nb && stat[mc + c] == ST_INACTIVE && mc + c != excl)
       {
-        double xi = xs[c];
-        double sl = xi - xl[c];
-        double su = xu[c] - xi;
+        const double xi = xv[c];
+        const double sl = xi - xl[c];
+        const double su = xu[c] - xi;
         if(sl < 0.0 && su < 0.0) bothneg = true;
         if(sl < best)
         {
@@ -1484,9 +1605,9 @@ struct GiCta
 #pragma unroll
     for(int off = 16; off >= 1; off >>= 1)
     {
-      double ov = __shfl_xor_sync(JRLQP_FULL, best, off);
-      double ocx = __shfl_xor_sync(JRLQP_FULL, bestcx, off);
-      int oc = __shfl_xor_sync(JRLQP_FULL, code, off);
+      const double ov = __shfl_xor_sync(JRLQP_FULL, best, off);
+      const double ocx = __shfl_xor_sync(JRLQP_FULL, bestcx, off);
+      const int oc = __shfl_xor_sync(JRLQP_FULL, code, off);
       if(ov < best || (ov == best && oc < code))
       {
         best = ov;
@@ -1494,42 +1615,41 @@ struct GiCta
         code = oc;
       }
     }
-    unsigned anyneg = __ballot_sync(JRLQP_FULL, bothneg);
-    if(TW > 1)
+    const unsigned anyneg = __ballot_sync(JRLQP_FULL, bothneg);
+    // lane 0's view is published (with NaN inputs the lanes may disagree: one lane decides)
+    if(lane == 0)
     {
-      if(lane == 0)
-      {
-        scr[2 + 2 * warp] = best;
-        scr[3 + 2 * warp] = bestcx;
-        iscr[2 * warp] = code;
-        iscr[2 * warp + 1] = anyneg != 0u;
-      }
-      sync();
-      best = scr[2];
-      bestcx = scr[3];
-      code = iscr[0];
-      int neg = iscr[1];
+      scr[2 + 2 * sw] = best;
+      scr[3 + 2 * sw] = bestcx;
+      iscr[2 * sw] = code;
+      iscr[2 * sw + 1] = anyneg != 0u;
+    }
+  }
+
+  // Every thread, after the barrier that follows scan_partial: the selected constraint, and its c.x for
+  // computeStepLength_ (x is unchanged between the two; same dot4 => same bits). xcur: the current x, for the exact
+  // sequential restatement used when some constraint has both slacks negative (bl > bu).
+  template<int NSW>
+  __device__ __forceinline__ Sel scan_combine(double & cx_sel)
+  {
+    double best = scr[2];
+    double bestcx = scr[3];
+    int code = iscr[0];
+    int neg = iscr[1];
 #pragma unroll
-      for(int w = 1; w < TW; ++w)
-      {
-        double ov = scr[2 + 2 * w];
-        int oc = iscr[2 * w];
-        neg |= iscr[2 * w + 1];
-        if(ov < best || (ov == best && oc < code))
-        {
-          best = ov;
-          bestcx = scr[3 + 2 * w];
-          code = oc;
-        }
-      }
-      anyneg = neg;
-    }
-    else
+    for(int w = 1; w < NSW; ++w)
     {
-      code = __shfl_sync(JRLQP_FULL, code, 0); // keep control flow uniform even with NaN inputs
-      bestcx = __shfl_sync(JRLQP_FULL, bestcx, 0);
+      const double ov = scr[2 + 2 * w];
+      const int oc = iscr[2 * w];
+      neg |= iscr[2 * w + 1];
+      if(ov < best || (ov == best && oc < code))
+      {
+        best = ov;
+        bestcx = scr[3 + 2 * w];
+        code = oc;
+      }
     }
-    if(anyneg)
+    if(neg)
     {
       Sel s = select_sequential(n, mc, nb, Cb, ldC, xs, bl, bu, xl, xu, stat);
       cx_sel = s.p < 0 ? 0.0 : (s.p < mc ? dot4_uniform(n, Cb + (long long)s.p * ldC, xs) : xs[s.p - mc]);
@@ -1624,92 +1744,78 @@ struct GiCta
     PH_MARK(4); // z
   }
 
-  // r = R^-1 d(0:q): column-oriented back substitution with true division, one warp, rows over
-  // the lanes (W slots). The quotient w_k / R(k,k) comes from the reciprocal kept in rinv[k]
-  // (div_rcp: 3 dependent FMAs, proven correctly rounded, stock division otherwise).
+  // r = R^-1 d(0:q): column-oriented back substitution with true division (r_k = w_k / R(k,k), then
+  // w_i = fma(-r_k, R(i,k), w_i) for i < k, k descending), one warp, rows over the lanes (W slots).
+  //
+  // What bounds it is the latency of one link, so the loop carries only what is serial:
+  //  * the pivot value is kept UNIFORM: while link k is being divided, every lane already holds w_{k-1} as it was
+  //    before link k (one shuffle, issued ahead of the quotient), and applies link k's update to it itself
+  //    (wp = fma(-r_k, R(k-1,k), w_{k-1}) — the very operation lane k-1 performs on its own row, hence the same
+  //    bits). The dependent chain of a link is the quotient (3 FMAs) + 1 FMA; the shuffle is off the chain;
+  //  * the quotient comes from the reciprocal kept in rinv[k] (div_rcp), and its proof of correct rounding is NOT
+  //    evaluated in the loop: lane k's row is never touched after its pivot, so after the loop lane k still holds
+  //    the dividend w_k, redoes its own quotient (same inputs, same bits) and checks the proof — all links at
+  //    once. If one proof is declined (rare) the pass is redone with the stock division.
   __device__ __forceinline__ void back_substitution()
   {
     double w[W], rr[W];
-#pragma unroll
-    for(int s = 0; s < W; ++s)
+    bool exact = false;
+#pragma unroll 1
+    for(;;)
     {
-      w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
-      rr[s] = 0.0;
-    }
-    // Fast pass: every quotient from the stored reciprocal, its proof accumulated in `allok` instead of
-    // being branched on (the branch would sit on the dependent chain). In the rare case one proof is
-    // declined the pass is redone with the stock division.
-    bool allok = true;
-#pragma unroll 1
-    for(int pass = 0; pass < 2; ++pass)
-    {
-      if(pass == 1)
-      {
-        if(allok) break;
 #pragma unroll
-        for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
-      }
-      // (prefetching the operands of link k - 1 ahead of the dependent part of link k was measured twice — with a
-      // rotating register set, -9 % at n = 50, and with two alternating sets, -6 %: profiles/r01n_ab_A.txt, r01o_ab_A.txt)
-      int k = q - 1;
-      // W >= 3: links k >= 32 touch the rows of every slot; links k < 32 only the rows of slot 0, and the pivot sits in
-      // slot 0: that loop carries one slot. Measured (profiles/r01zi_ab_*.txt): +4 % at n = 128, but -2.2 % at n = 50
-      // and -5.7 % at n = 20, where the second loop only adds code: compiled for the wide CTAs alone.
-      constexpr bool BSPLIT = JRLQP_OPT_BSPLIT && W >= 3;
-      const int klow = BSPLIT ? 32 : 0;
-#pragma unroll 1
-      for(; k >= klow; --k)
+      for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
+      if(q > 0)
       {
+        int k = q - 1;
         const double * Rk = Rp + colR(k);
-        const double rkk = Rk[k], ri = rinv[k];
-        double col[W];
-#pragma unroll
-        for(int s = 0; s < W; ++s) col[s] = Rk[min(lane + 32 * s, k)];
-        const double wk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31);
-        double rk;
-        if(pass == 0)
-        {
-          bool ok;
-          rk = div_rcp(wk, rkk, ri, ok);
-          allok = allok && ok;
-        }
-        else
-          rk = wk / rkk;
-#pragma unroll
-        for(int s = 0; s < W; ++s)
-        {
-          if(32 * s >= k + 1) continue; // slot entirely above row k
-          int r = lane + 32 * s;
-          if(r == k)
-            rr[s] = rk;
-          else if(r < k)
-            w[s] = fma(-rk, col[s], w[s]);
-        }
-      }
-      if(BSPLIT)
-      {
+        double wp = ds[k];
 #pragma unroll 1
-      for(; k >= 0; --k)
-      {
-        const double * Rk = Rp + colR(k);
-        const double rkk = Rk[k], ri = rinv[k];
-        const double col0 = Rk[min(lane, k)];
-        const double wk = __shfl_sync(JRLQP_FULL, w[0], k);
-        double rk;
-        if(pass == 0)
+        for(; k >= 0; --k)
         {
-          bool ok;
-          rk = div_rcp(wk, rkk, ri, ok);
-          allok = allok && ok;
+          const double rkk = Rk[k], ri = rinv[k];
+          const double rnk = Rk[k - 1]; // R(k-1, k); k == 0: an unused read of the word before R
+          double col[W];
+#pragma unroll
+          for(int s = 0; s < W; ++s) col[s] = Rk[lane + 32 * s]; // rows >= k: an unused read past the column
+          const double wn = __shfl_sync(JRLQP_FULL, pick<W>(w, (k - 1) >> 5), (k - 1) & 31);
+          double rk;
+          if(!exact)
+          {
+            const double q0 = wp * ri;
+            const double e = fma(-rkk, q0, wp);
+            rk = fma(e, ri, q0);
+          }
+          else
+            rk = wp / rkk;
+#pragma unroll
+          for(int s = 0; s < W; ++s)
+            if(lane + 32 * s < k) w[s] = fma(-rk, col[s], w[s]);
+          wp = fma(-rk, rnk, wn);
+          Rk -= k;
         }
-        else
-          rk = wk / rkk;
-        if(lane == k)
-          rr[0] = rk;
-        else if(lane < k)
-          w[0] = fma(-rk, col0, w[0]);
       }
+      bool ok = true;
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+      {
+        const int r = lane + 32 * s;
+        rr[s] = 0.0;
+        if(r < q)
+        {
+          const double y = Rp[colR(r) + r];
+          if(exact)
+            rr[s] = w[s] / y;
+          else
+          {
+            bool okk;
+            rr[s] = div_rcp(w[s], y, rinv[r], okk);
+            ok = ok && okk;
+          }
+        }
       }
+      if(exact || __all_sync(JRLQP_FULL, ok)) break;
+      exact = true;
     }
 #pragma unroll
     for(int s = 0; s < W; ++s)
@@ -1718,14 +1824,14 @@ struct GiCta
 
   // Givens recurrence of the add that may follow (see givens_chain above)
   static constexpr bool SPLIT_CHAIN = JRLQP_OPT_CS && W > 1;
-  __device__ __forceinline__ void givens_recurrence() { givens_chain<SPLIT_CHAIN>(q, n, lane, ds, gcs, gc, gs, gk, scr); }
+  __device__ __forceinline__ void givens_recurrence() { givens_chain<SPLIT_CHAIN>(q, n, lane, ds, gcs, gc, gs, gk, scr, reinterpret_cast<double *>(gcs) + T); }
 
   // ------------------------------------------------------------------------------------------
-  // computeStepLength_ (src/GoldfarbIdnaniSolver.cpp:150-219), incl. the activationStatus(k) quirk.
-  // Evaluated redundantly by every warp (no cross-warp traffic). nz receives
-  // ConstraintNormal::dot(z) (src/GoldfarbIdnaniSolver.cpp:289-293); zpos tells whether ||z|| > 1e-14.
+  // computeStepLength_ (src/GoldfarbIdnaniSolver.cpp:150-219), incl. the activationStatus(k) quirk, in two halves
+  // that different warps can evaluate concurrently: len_t1 needs r (after the back substitution), len_z only z and x.
   // ------------------------------------------------------------------------------------------
-  __device__ void step_length(Sel sc, bool cx_valid, double cx_in, double & t1, double & t2, int & l, double & nz, bool & zpos, const bool need_t1 = true)
+  // t1: first minimum of u[k]/r[k] over r[k] > 0 and status_[k] not in {EQUALITY, FIXED}; one warp.
+  __device__ __forceinline__ void len_t1(double & t1, int & l, const bool need_t1)
   {
     const double big = P.big_bnd;
     t1 = big;
@@ -1733,7 +1839,6 @@ struct GiCta
     // (addInitialConstraint takes the exact step onto the constraint: no ratio test, src/GoldfarbIdnaniSolver.cpp:295-338)
     if(need_t1 || !(JRLQP_OPT_T1 && W == 2)) // measured: +1.0 % at W = 2, -2.2 % at W = 1, -0.7 % at W = 4 (profiles/r01z_ab_*.txt)
     {
-      // t1: first minimum of u[k]/r[k] over r[k] > 0 and status_[k] not in {EQUALITY, FIXED}
       double bt = big;
       int bl_ = JRLQP_NONE;
 #pragma unroll
@@ -1774,7 +1879,11 @@ struct GiCta
         l = bl_;
       }
     }
+  }
 
+  // t2 = (b - c.x) / (c.z) if ||z|| > 1e-14, nz = ConstraintNormal::dot(z) (src/GoldfarbIdnaniSolver.cpp:289-293); one warp.
+  __device__ __forceinline__ void len_z(Sel sc, bool cx_valid, double cx_in, double & t2, double & nz, bool & zpos)
+  {
     // ||z|| with the dot32 order: lane accumulates k = lane, lane+32, ... then the xor butterfly
     double zz = 0.0;
     for(int k = lane; k < n; k += 32)
@@ -1784,7 +1893,7 @@ struct GiCta
     }
     zpos = sqrt(warp_sum32(zz)) > 1e-14;
 
-    t2 = big;
+    t2 = P.big_bnd;
     double cz;
     if(sc.st < ST_LOWER_BOUND)
     {
@@ -2116,13 +2225,25 @@ struct GiCta
 
     int status = TS_MAX_ITER_REACHED;
     bool skip = false;
-    bool have_sel = false; // the constraint of this iteration was already selected at the end of the previous one
+    bool have_sel = false; // the constraint of this iteration was already selected during the previous one
     Sel sc{-1, ST_INACTIVE};
     double cx_sel = 0.0;
     const double big = P.big_bnd;
-    // Decisions are taken by warp 0 (while warp 1 runs the Givens recurrence) and published here.
-    int * dec = iscr + 2 * W; // [0] add, [1] l, [2] status on break (-1: none), [5] select the next constraint now
-    double * decd = scr + 13; // [0] f
+    // Warp roles inside a step: warp 0 runs the back substitution, the ratio test, the decision and the
+    // step; warp CW the Givens recurrence of the add that may follow. The two recurrences are about equally long, so
+    //  * W <= 2: the z-dependent half of the step length stays on warp 0 and the next constraint scan is done by all
+    //    the threads once the step is taken (x final);
+    //  * W >= 3 (SPEC): warps [2, W) have no recurrence to run: they evaluate the z-dependent half of the step length
+    //    and then — speculatively, at the point x + t2 z a full step would reach — the constraint scan of the NEXT
+    //    iteration, concurrently with the recurrences; the result is simply discarded when the step turns out to be
+    //    partial.
+    constexpr bool SPEC = W >= 3;
+    constexpr int CW = W > 1 ? 1 : 0;
+    constexpr int SW = SPEC ? 2 : 0; // first scan warp
+    constexpr int NSW = SPEC ? W - 2 : W; // number of scan warps
+    int * dec = iscr + 2 * W; // [0] add, [1] l, [2] status on break (-1: none), [3] ||z|| > 1e-14, [4] speculative scan done, [5] the next selection is wanted
+    double * decd = scr + 13; // [0] f, [1] t2, [2] n+.z
+    double * xs2 = cv; // speculative x: the staged normal is dead once len_z has read it
 #pragma unroll 1
     for(;;)
     {
@@ -2138,125 +2259,212 @@ struct GiCta
           break;
         }
       }
+      bool sel_only = false; // this pass only selects (no selection was made ahead: first iteration without equalities)
       if(!pre)
       {
         if(it >= P.max_iter) break; // MAX_ITER_REACHED
         if(!skip)
         {
-          PH_MARK(11);
-          if(!have_sel) sc = select<W>(cx_sel);
-          PH_MARK(1);
-          if(sc.st == ST_INACTIVE)
+          if(!have_sel)
+            sel_only = true;
+          else if(sc.st == ST_INACTIVE)
           {
             status = TS_SUCCESS;
             break;
           }
         }
       }
-      // will the step after this one need a fresh selection (i.e. is the pre-activation phase over)?
-      bool more_pre = false;
-      for(int c = cursor; c < m; ++c)
-        if(eqf[c])
-        {
-          more_pre = true;
-          break;
-        }
-      if(pre || !skip)
+      bool add = false;
+      int l = 0;
+      bool scan_now = sel_only; // the scan warps run the scan in this pass
+      const double * xv = xs; // ... of this point
+      int excl = -1;
+      if(!sel_only)
       {
-        if(tid == 0) us[q] = 0.0; // published by the barriers of compute_step
-      }
-      PH_MARK(11);
-      compute_step(sc);
-      // ---- warp 0: r = R^-1 d1, step length, the step itself and, when a constraint is added, the
-      //      bookkeeping of the add;
-      //      warp 1 (warp 0 when W == 1): the Givens recurrence of the add that may follow.
-      if(warp == 0)
-      {
-        back_substitution();
-        PH_MARK(5);
-        double t1, t2, nz;
-        int l;
-        bool zpos;
-        step_length(sc, !pre && !skip, cx_sel, t1, t2, l, nz, zpos, !pre);
-        PH_MARK(7);
-        double t;
-        bool primal = true, add = true;
-        int brk = -1;
-        if(pre)
-          t = zpos ? t2 : 0.0; // exact step onto the constraint (src/GoldfarbIdnaniSolver.cpp:307-322)
-        else
-        {
-          t = t2 < t1 ? t2 : t1; // std::min(t1, t2)
-          if(t >= big)
-            brk = TS_INFEASIBLE;
-          else if(t2 >= big)
-            primal = add = false; // dual-only step, then drop
-          else
-            add = t == t2; // full step -> add ; partial step -> drop
-        }
-        int nvalid = 0;
-        if(brk < 0)
-        {
-          take_step(t, nz, primal);
-          PH_MARK(8);
-          if(add)
+        // will the step after this one need a fresh selection (i.e. is the pre-activation phase over)?
+        bool more_pre = false;
+        for(int c = cursor; c < m; ++c)
+          if(eqf[c])
           {
-            // DualSolver::addConstraint bookkeeping (src/DualSolver.cpp:231-235)
+            more_pre = true;
+            break;
+          }
+        const bool want_next = !more_pre && (pre || it + 1 < P.max_iter);
+        if(pre || !skip)
+        {
+          if(tid == 0) us[q] = 0.0; // published by the barriers of compute_step
+        }
+        PH_MARK(11);
+        compute_step(sc);
+        const int zw = (SPEC && want_next) ? SW : 0; // the warp that evaluates the z-dependent half of the step length
+        double t2 = 0.0, nz = 0.0;
+        bool zpos = false;
+        if(warp == zw)
+        {
+          len_z(sc, !pre && !skip, cx_sel, t2, nz, zpos);
+          PH_MARK(7);
+          if(SPEC && zw != 0)
+          {
+            const double ts = pre ? (zpos ? t2 : 0.0) : t2; // the length of a full step (pre-activation: the exact step)
+            const bool spec = ts < big;
+            __syncwarp(); // cv has been read by every lane
+#pragma unroll
+            for(int s = 0; s < W; ++s)
+            {
+              const int r = lane + 32 * s;
+              if(r < n) xs2[r] = fma(ts, zs[r], xs[r]);
+            }
             if(lane == 0)
             {
-              alist[q] = sc.p;
-              stat[sc.p] = (signed char)sc.st;
+              decd[1] = t2;
+              decd[2] = nz;
+              dec[3] = zpos;
+              dec[4] = spec;
             }
-            nvalid = (!more_pre && (pre || it + 1 < P.max_iter)) ? 1 : 0;
+            asm volatile("bar.arrive 1, 64;" ::: "memory"); // hand t2, n+.z over to warp 0 (which waits with bar.sync 1)
+            if(NSW > 1) asm volatile("bar.sync 2, %0;" ::"n"(32 * (NSW > 1 ? NSW : 1)) : "memory"); // x + t2 z is visible to the other scan warps
+            scan_now = spec;
           }
         }
-        if(lane == 0)
+        else if(SPEC && NSW > 1 && zw != 0 && warp > SW)
         {
-          dec[0] = add;
-          dec[1] = l;
-          dec[2] = brk;
-          dec[5] = nvalid;
-          decd[0] = f;
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * (NSW > 1 ? NSW : 1)) : "memory");
+          scan_now = dec[4] != 0;
+        }
+        if(SPEC)
+        {
+          xv = xs2;
+          excl = sc.p; // the constraint being added is still INACTIVE in stat (or being written by warp 0)
+        }
+        // ---- warp 0: r = R^-1 d1, step length, the step itself and, when a constraint is added, the
+        //      bookkeeping of the add
+        if(warp == 0)
+        {
+          back_substitution();
+          PH_MARK(5);
+          double t1;
+          len_t1(t1, l, !pre);
+          if(SPEC && zw != 0)
+          {
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            t2 = decd[1];
+            nz = decd[2];
+            zpos = dec[3] != 0;
+          }
+          PH_MARK(7);
+          double t;
+          bool primal = true;
+          add = true;
+          int brk = -1;
+          if(pre)
+            t = zpos ? t2 : 0.0; // exact step onto the constraint (src/GoldfarbIdnaniSolver.cpp:307-322)
+          else
+          {
+            t = t2 < t1 ? t2 : t1; // std::min(t1, t2)
+            if(t >= big)
+              brk = TS_INFEASIBLE;
+            else if(t2 >= big)
+              primal = add = false; // dual-only step, then drop
+            else
+              add = t == t2; // full step -> add ; partial step -> drop
+          }
+          int nvalid = 0;
+          if(brk < 0)
+          {
+            take_step(t, nz, primal);
+            PH_MARK(8);
+            if(add)
+            {
+              // DualSolver::addConstraint bookkeeping (src/DualSolver.cpp:231-235)
+              if(lane == 0)
+              {
+                alist[q] = sc.p;
+                stat[sc.p] = (signed char)sc.st;
+              }
+              nvalid = want_next ? 1 : 0;
+            }
+          }
+          if(lane == 0)
+          {
+            dec[0] = add;
+            dec[1] = l;
+            dec[2] = brk;
+            dec[5] = nvalid;
+            decd[0] = f;
+          }
+        }
+        if(warp == CW)
+        {
+          givens_recurrence();
+          PH_MARK(6);
+        }
+        if(!SPEC)
+        {
+          // every thread learns the decision; the scan (if wanted) then runs on the final x
+          sync();
+          PH_MARK(11);
+          add = dec[0] != 0;
+          l = dec[1];
+          f = decd[0];
+          if(dec[2] >= 0)
+          {
+            status = dec[2];
+            break;
+          }
+          scan_now = add && dec[5] != 0;
+          if(add && SPLIT_CHAIN)
+          {
+            // the (c, s) pairs of the sweep, one rotation per thread (second division of makeGivens); published by the
+            // barrier below
+            if(tid >= q && tid <= n - 2) gcs[tid] = givens_cs(gk[tid], gc[tid], gs[tid]);
+          }
         }
       }
-      if(warp == (W > 1 ? 1 : 0))
+      // ---- the constraint scan (one call site): of the current x when this pass only selects or when every thread
+      //      takes part (W <= 2), of the speculative x on the scan warps otherwise
+      if(warp >= SW && scan_now)
       {
-        givens_recurrence();
-        PH_MARK(6);
+        scan_partial<NSW>(xv, excl, warp - SW);
+        PH_MARK(1);
       }
       sync();
       PH_MARK(11);
-      const bool add = dec[0] != 0;
-      const int l = dec[1];
-      const int brk = dec[2];
-      f = decd[0];
-      if(brk >= 0)
+      if(sel_only)
       {
-        status = brk;
-        break;
+        sc = scan_combine<NSW>(cx_sel);
+        have_sel = true;
+        continue;
       }
-      have_sel = dec[5] != 0;
+      if(SPEC)
+      {
+        add = dec[0] != 0;
+        l = dec[1];
+        f = decd[0];
+        if(dec[2] >= 0)
+        {
+          status = dec[2];
+          break;
+        }
+        // a full step reached exactly the point the scan warps tested: x + t z with t == t2 (same fma, same bits)
+        have_sel = add && dec[5] != 0 && dec[4] != 0;
+      }
+      else
+        have_sel = scan_now;
       if(add)
       {
-        if(SPLIT_CHAIN)
-        {
-          // the (c, s) pairs of the sweep, one rotation per thread (second division of makeGivens)
-          if(tid >= q && tid <= n - 2) gcs[tid] = givens_cs(gk[tid], gc[tid], gs[tid]);
-          if(!have_sel) sync(); // otherwise the barrier inside select() publishes the table
-        }
-        // x and the active set are final: the next violated constraint can be selected now, by the
-        // whole CTA, before the rotations are applied (they do not touch x)
-        Sel nxt{-1, ST_INACTIVE};
-        double cxn = 0.0;
-        if(have_sel) nxt = select<W>(cxn);
-        PH_MARK(1);
-        add_constraint();
-        PH_MARK(9);
         if(have_sel)
         {
-          sc = nxt;
+          double cxn;
+          sc = scan_combine<NSW>(cxn);
           cx_sel = cxn;
         }
+        if(SPEC && SPLIT_CHAIN)
+        {
+          if(tid >= q && tid <= n - 2) gcs[tid] = givens_cs(gk[tid], gc[tid], gs[tid]);
+          sync();
+        }
+        add_constraint();
+        PH_MARK(9);
       }
       else
       {
@@ -2343,6 +2551,8 @@ __global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W
   extern __shared__ __align__(16) double smem[];
   GiCta<W, STAGE_C, WARM> cta(p, smem);
   unsigned long long * ticket = reinterpret_cast<unsigned long long *>(smem + p.off_scr + 12);
+  // the constraint scan reads x (and the speculative x kept in cv) in whole 16-byte pairs: the padding stays zero
+  if((int)threadIdx.x >= p.n) cta.xs[threadIdx.x] = cta.cv[threadIdx.x] = 0.0;
   int ct_slot = -1;
   if(!STAGE_C && (W >= 3 || JRLQP_CT_ALLW) && p.ct != nullptr && p.mc > 0)
   {

@@ -1037,7 +1037,7 @@ struct GiLarge
         }
       }
       else if(warp == 1)
-        givens_chain(q, n, lane, ds, gcs, gc, gs, gk, scr);
+        givens_chain(q, n, lane, ds, gcs, gc, gs, gk, scr, reinterpret_cast<double *>(gcs) + ((n + 3) & ~3));
       sync();
       const bool add = dec[0] != 0;
       const int l = dec[1];

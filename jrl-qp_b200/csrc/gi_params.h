@@ -91,7 +91,7 @@ struct GiParams
   int ldcs; // leading dimension of the staged C (odd), if staged
   int npad; // threads per CTA (>= n)
   int off_R, off_x, off_z, off_d, off_r, off_u, off_cv, off_gc, off_gs, off_gcs, off_ldiag, off_rinv, off_scr, off_C; // offsets in doubles
-  int off_alist, off_gk, off_iscr, off_stat, off_eq;
+  int off_alist, off_gk, off_iscr, off_stat, off_eq, off_il;
   int off_V, off_bact, off_hco, off_alpha; // warm-start kernels only (offsets in doubles) // offsets in doubles of the int / int8 arrays
 };
 

@@ -25,10 +25,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="A")
     ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--no-build", action="store_true", help="use the _build/libjrlqp_b200_timing.so built beforehand (no nvcc run on the GPU box)")
     args = ap.parse_args()
     out = os.path.join(B.OUT, "libjrlqp_b200_timing.so")
     srcs = B._listdir(B.CSRC, (".cu",))
-    subprocess.run([B.NVCC] + B.NVCC_FLAGS + ["-DJRLQP_PHASE_TIMING"] + srcs + ["-o", out], check=True, capture_output=True)
+    if not (args.no_build and os.path.exists(out)):
+        subprocess.run([B.NVCC] + B.NVCC_FLAGS + ["-DJRLQP_PHASE_TIMING"] + srcs + ["-o", out], check=True, capture_output=True)
     S.library_path = lambda: out
     S._lib = None
     ch = {"A": P.config_A, "B": P.config_B, "D": P.config_D}[args.config]()
