@@ -93,13 +93,9 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage, bool warm = fal
   o += np + 2;
   L.off_cv = o;
   o += np;
-  L.off_gc = o;
-  o += np;
-  L.off_gs = o;
-  o += np;
-  o += o & 1; // 16-byte alignment of the (c, s) pairs
-  L.off_gcs = o;
-  o += 2 * np;
+  o += o & 1; // 16-byte alignment of the per-link records of the Givens sweep
+  L.off_gc = L.off_gs = L.off_gcs = o; // (one array of 32-byte records: see GiCta::givens_recurrence)
+  o += 4 * np;
   L.off_ldiag = o;
   o += np;
   L.off_rinv = o;
@@ -110,8 +106,7 @@ Layout make_layout(int n, int mc, int nb, int warps, bool stage, bool warm = fal
   o += stage ? mc * L.ldcs : 0;
   L.off_alist = o;
   o += np / 2 + 1;
-  L.off_gk = o;
-  o += np / 2 + 1;
+  L.off_gk = o; // (unused: the branch taken lives in the records)
   L.off_iscr = o;
   o += 8;
   L.off_stat = o;

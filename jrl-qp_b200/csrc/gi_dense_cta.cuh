@@ -24,7 +24,7 @@
 //        triangle, lower cleared. Row-major + odd ld makes both access patterns conflict-free:
 //        threads over columns (d = J^T n+) and threads over rows (z = J2 d2, column rotations).
 //   Rp   packed upper-triangular R, column k at k(k+1)/2.
-//   xs, zs, ds, rs, us, cv (selected normal), gc/gs (Givens table), ldiag, alist, stat, scratch.
+//   xs, zs, ds, rs, us, cv (selected normal), grec (Givens sweep records), ldiag, alist, stat, scratch.
 //   Cs   optional staged copy of C (mc x ldcs, ldcs odd, one normal per row).
 // Every floating-point result is produced in the canonical order that oracle/gi_oracle.cpp documents
 // (dot4 / dot32 / fma axpy / Eigen makeGivens): results are bit-identical to the oracle whatever W.
@@ -335,23 +335,80 @@ __device__ __forceinline__ double2 givens_cs(const int kind8, const double a, co
   return make_double2(c, sn);
 }
 
+// One link of the Givens recurrence outside the straight-line fast path (a zero operand, |d[i]| > |rho|, or the
+// careful pass after a declined proof): Eigen's makeGivens branches, literally. Out of line (cold).
+struct GivensLink
+{
+  double a, u, r;
+  int kind;
+};
+__device__ __noinline__ GivensLink givens_link_slow(const double p, const double rho, const double rp, const bool have_rp)
+{
+  GivensLink g;
+  if(rho == 0.0)
+  {
+    g.kind = 0;
+    g.a = p;
+    g.u = 1.0;
+    g.r = fabs(p);
+  }
+  else if(p == 0.0)
+  {
+    g.kind = 1;
+    g.a = rho;
+    g.u = 1.0;
+    g.r = fabs(rho);
+  }
+  else
+  {
+    const bool pg = fabs(p) > fabs(rho);
+    g.kind = pg ? 2 : 3;
+    const double num = pg ? rho : p, den = pg ? p : rho;
+    bool ok = false;
+    double a = 0.0;
+    if(pg && have_rp) a = div_rcp(num, den, rp, ok); // 1 / p was precomputed
+    if(!ok) a = num / den;
+    const double uu = sqrt(fma(a, a, 1.0));
+    g.a = a;
+    g.u = den < 0.0 ? -uu : uu;
+    g.r = den * g.u;
+  }
+  return g;
+}
+
+// ~ 1 / sqrt(x) to about 44 bits (hardware seed + one Newton step): all the seeds of the Givens recurrence need
+__device__ __forceinline__ double rsqrt_seed(const double x)
+{
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-(x * y0), y0, 1.0);
+  return fma(0.5 * y0, e, y0);
+}
+
 // SPLIT: the lane-parallel parts on either side of the recurrence (the reciprocals 1 / d[i] before it, the
 // (c, s) pairs after it) are done by the caller with all the threads of the CTA, off this warp's critical path.
-// gr: n doubles of scratch (the incoming rho of every link, for the deferred proof).
-template<bool SPLIT = false>
+// gr: n doubles of scratch (the incoming rho of every link, for the deferred proofs).
+//
+// Latency of one link is what matters here. Per link, Eigen's makeGivens needs t = num / den, u = sqrt(1 + t^2),
+// r = den u, with den = rho (the running value) in the common case |rho| >= |p|: a division and a square root that
+// depend on the previous link — about 20 dependent FP64 operations with the stock sequences, 12 with a reciprocal
+// carried along the recurrence (round 1). Here the link is cut to 7 dependent operations:
+//  * SEEDS, computed for all links at once before the recurrence: rho_j^2 is (up to rounding) the suffix sum
+//    S_j = d_j^2 + d_{j+1}^2 + ..., so rs_i = rsqrt(S_{i+1}) ~ 1 / rho_{i+1} and ys_i = rsqrt(1 + (d_i rs_i)^2) ~ 1 / u_i
+//    are known to ~45 bits without running the recurrence (one warp scan + two rsqrt per lane);
+//  * the link itself: t = p / rho by one correction of p rs_i (e = p - rho q0; t = q0 + e rs_i), s = 1 + t^2,
+//    u = sqrt(s) by one correction of s ys_i (g = s ys; u = g + (s - g^2) ys / 2), r = |rho| u;
+//  * PROOFS, evaluated for all links at once after the recurrence (one link per lane), that the quotient and the
+//    square root so obtained are the correctly rounded ones — exact remainder tests: |p - rho t| < |rho| ulp(t) / 2
+//    (see fp64_exact.cuh) and |s - u^2| < u ulp(u) (1 - 2^-41) (s - u^2 is exact for u within an ulp of the root, and
+//    u = RN(sqrt s) iff (u - ulp/2)^2 < s < (u + ulp/2)^2). The results therefore never depend on the seeds: if one
+//    proof is declined (rare: a seed off by more than ~2^-30, a result within 2^-90 of a rounding boundary) the
+//    chain is redone with every quotient and root taken literally;
+//  * every other case (|d[i]| > |rho|, a zero operand) leaves the straight-line fast path through one branch and
+//    is evaluated with precomputed 1 / d[i] or literally.
+template<bool SPLIT = false, int UNR = 2>
 __device__ __forceinline__ void givens_chain(const int q, const int n, const int lane, const double * ds, double2 * gcs, double * gc, double * gs, int * gk, double * scr, double * gr)
 {
-  // Latency of one link is what matters here. Per link, Eigen's makeGivens needs t = num / den,
-  // u = sqrt(1 + t^2), r = den u, with den = rho (the running value) in the common case
-  // |rho| >= |p|. The stock division and square root chain ~20 dependent FP64 operations; here
-  //  * a reciprocal of rho is carried along the recurrence (rr0 = |1/rho| * y1, y1 ~ 1/sqrt(1+t^2)
-  //    being a by-product of the square root), so that t costs 2 dependent FMAs after rho is known
-  //    (div_rcp with the product q0 = p * rr0 issued one link ahead);
-  //  * that quotient is PROVEN to be the correctly rounded one by an exact remainder test (see fp64_exact.cuh) which
-  //    is not evaluated in the loop: the loop stashes (t, rho) per link and, afterwards, every lane checks one link.
-  //    If a proof is declined (rare) the chain is redone with every quotient taken literally;
-  //  * every other case (|d[i]| > |rho|, a zero operand) leaves the straight-line fast path through one branch and
-  //    is evaluated with precomputed 1 / d[i] or literally.
   double * rpv = reinterpret_cast<double *>(gcs); // 1 / d[i]; gcs is only written after the chain
   if(!SPLIT)
   {
@@ -360,6 +417,43 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
     {
       rpv[i] = 1.0 / ds[i];
     }
+  }
+  // ---- seeds: element j = top - lane of d, chunks of 32 from the last element down; suffix sums by a warp scan.
+  //      The seeds of link i = j - 1 go where the loop will later stash (t, u) of that link: gc[i], gs[i] (the loop
+  //      reads the seeds of link i - 1 while it works on link i, and only then overwrites those of link i).
+  {
+    double carry = 0.0;
+#pragma unroll 1
+    for(int top = n - 1; top >= q; top -= 32)
+    {
+      const int j = top - lane;
+      const bool valid = j >= q;
+      const double dj = valid ? ds[j] : 0.0;
+      const double dm = valid ? ds[j - 1] : 0.0; // d of the link this element feeds (j == 0: an unused read of the padding before d)
+      double sc = dj * dj;
+#pragma unroll
+      for(int off = 1; off < 32; off <<= 1)
+      {
+        const double t = __shfl_up_sync(JRLQP_FULL, sc, off);
+        if(lane >= off) sc = sc + t;
+      }
+      const double S = carry + sc;
+      carry = __shfl_sync(JRLQP_FULL, S, 31);
+      double rsd = rsqrt_seed(S);
+      if(j == n - 1) rsd = dj < 0.0 ? -rsd : rsd; // the first rho is d[n-1] itself, sign included
+      const double t = dm * rsd;
+      const double ysd = rsqrt_seed(fma(t, t, 1.0));
+      if(valid)
+      {
+        if(j > q)
+        {
+          gc[j - 1] = rsd;
+          gs[j - 1] = ysd;
+        }
+        else
+          scr[11] = rsd; // ~ 1 / rho_q: reciprocal of the new diagonal entry of R (an approximation is all rinv needs)
+      }
+    }
     __syncwarp();
   }
   bool careful = false;
@@ -367,63 +461,33 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
   for(;;)
   {
     double rho = ds[n - 1];
-    double rrR = rpv[n - 1]; // reciprocal of rho, refined
-    double rrE = rrR; // reciprocal of rho available before rho itself (feeds q0 and the correction)
     int i = n - 2;
     double p = ds[max(i, 0)];
-    double q0s = p * rrE; // first product of the quotient p / rho, issued ahead
-#pragma unroll 2
+    double rsi = gc[max(i, 0)], ysi = gs[max(i, 0)];
+    double q0s = p * rsi; // first product of the quotient p / rho, issued ahead
+#pragma unroll UNR
     for(; i >= q; --i)
     {
-#if JRLQP_OPT_PN
-      const double pn = ds[i - 1]; // operand of the next link (i == 0: ds[-1] is the padding of the vector stored before d; unused)
-#else
-      const double pn = ds[max(i - 1, 0)]; // operand of the next link
-#endif
-      // ---- fast path: t = p / rho, straight line
+      // operands of the next link (i == 0: unused reads of the padding stored before the vectors)
+      const double pn = ds[i - 1], rsn = gc[i - 1], ysn = gs[i - 1];
+      // ---- fast path: t = p / rho, u = sqrt(1 + t^2), r = |rho| u, straight line
       const double e3 = fma(-rho, q0s, p);
-      double a = fma(e3, rrE, q0s);
-      double y1;
-      const double us = sqrt_rsqrt(fma(a, a, 1.0), y1);
+      double a = fma(e3, rsi, q0s);
+      const double s = fma(a, a, 1.0);
+      const double g = s * ysi;
+      const double rem = fma(-g, g, s);
+      const double us = fma(rem, 0.5 * ysi, g);
       double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
-      double rr0 = fabs(rrR) * y1; // ~ 1 / r, known before r
-      double rrn = fma(rr0, fma(-r, rr0, 1.0), rr0);
       double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
-      int kind = 3 | 8; // bit 3: the quotient of this link is to be proven after the loop
+      int kind = 3 | 8; // bit 3: the quotient and the root of this link are to be proven after the loop
       const bool fast = !careful && fabs(p) <= fabs(rho) && p != 0.0;
       if(!fast)
       {
-        const double rp = rpv[i];
-        if(rho == 0.0)
-        {
-          kind = 0;
-          a = p;
-          u = 1.0;
-          r = fabs(p);
-          rr0 = fabs(rp);
-        }
-        else if(p == 0.0)
-        {
-          kind = 1;
-          a = rho;
-          u = 1.0;
-          r = fabs(rho);
-          rr0 = fabs(rrR);
-        }
-        else
-        {
-          const bool pg = fabs(p) > fabs(rho);
-          kind = pg ? 2 : 3;
-          const double num = pg ? rho : p, den = pg ? p : rho;
-          bool ok = false;
-          if(pg) a = div_rcp(num, den, rp, ok); // 1 / p was precomputed
-          if(!ok) a = num / den;
-          const double uu = sqrt(fma(a, a, 1.0));
-          u = den < 0.0 ? -uu : uu;
-          r = den * u;
-          rr0 = 1.0 / r;
-        }
-        rrn = rr0;
+        const GivensLink g = givens_link_slow(p, rho, rpv[i], true);
+        a = g.a;
+        u = g.u;
+        r = g.r;
+        kind = g.kind;
       }
       if(lane == 0)
       {
@@ -434,34 +498,33 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
         gr[i] = rho;
       }
       rho = r;
-      rrR = rrn;
-      rrE = rr0;
       p = pn;
-      q0s = pn * rr0;
+      rsi = rsn;
+      ysi = ysn;
+      q0s = pn * rsn;
     }
-    if(lane == 0)
-    {
-      scr[11] = rrR; // ~ 1 / rho: reciprocal of the new diagonal entry of R
-      scr[10] = rho;
-    }
+    if(lane == 0) scr[10] = rho;
     __syncwarp();
     if(careful) break;
-    // ---- deferred proofs, one link per lane: t == RN(p / rho) iff |p - rho t| < |rho| ulp(t) / 2, t not a power of
-    //      two, nothing near underflow
+    // ---- deferred proofs, one link per lane
     bool ok = true;
 #pragma unroll 1
     for(int j = q + lane; j <= n - 2; j += 32)
     {
       if(gk[j] & 8)
       {
-        const double a = gc[j], rh = gr[j];
+        const double a = gc[j], rh = gr[j], us = fabs(gs[j]);
+        // t == RN(p / rho) iff |p - rho t| < |rho| ulp(t) / 2, t not a power of two, nothing near underflow
         const double e2 = fma(-rh, a, ds[j]); // exact remainder
         const int ahi = __double2hiint(a);
         const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
         const double tol = fabs(rh) * hu;
         const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
+        // u == RN(sqrt(s)), s = 1 + t^2 in [1, 2] (so ulp(u) = 2^-52): |s - u^2| < u 2^-52 (1 - 2^-41)
+        const double s = fma(a, a, 1.0);
+        const double rem2 = fma(-us, us, s);
 #ifndef JRLQP_DIAG_NOPROOF
-        ok = ok && fabs(e2) < tol && tol > 1e-270 && !pow2;
+        ok = ok && fabs(e2) < tol && tol > 1e-270 && !pow2 && fabs(rem2) < us * 0x1.ffffffffffp-53 && us >= 1.0 && us < 2.0;
 #endif
       }
     }
@@ -476,6 +539,39 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
       gcs[i] = givens_cs(gk[i], gc[i], gs[i]);
     }
   }
+}
+
+// r = R^-1 d(0:q) with the stock division in every link: the fallback of GiCta::back_substitution when one of its
+// deferred proofs is declined (rare). Out of line: the instruction cache holds the fast loops only.
+template<int W>
+__device__ __noinline__ void back_substitution_exact(const int q, const int lane, const double * ds, const double * Rp, double * rs)
+{
+  double w[W], rr[W];
+#pragma unroll
+  for(int s = 0; s < W; ++s)
+  {
+    w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
+    rr[s] = 0.0;
+  }
+#pragma unroll 1
+  for(int k = q - 1; k >= 0; --k)
+  {
+    const double * Rk = Rp + ((k * (k + 1)) >> 1);
+    const double wk = __shfl_sync(JRLQP_FULL, pick<W>(w, k >> 5), k & 31);
+    const double rk = wk / Rk[k];
+#pragma unroll
+    for(int s = 0; s < W; ++s)
+    {
+      const int r = lane + 32 * s;
+      if(r == k)
+        rr[s] = rk;
+      else if(r < k)
+        w[s] = fma(-rk, Rk[r], w[s]);
+    }
+  }
+#pragma unroll
+  for(int s = 0; s < W; ++s)
+    if(lane + 32 * s < q) rs[lane + 32 * s] = rr[s];
 }
 
 struct Sel
@@ -600,10 +696,9 @@ struct GiCta
   const GiParams & P;
   const int tid, lane, warp;
   const int n, mc, nb, m, ldj;
-  double *Jb, *Rp, *xs, *zs, *ds, *rs, *us, *cv, *gc, *gs, *ldiag, *rinv, *Cs, *scr;
-  double2 * gcs; // (c, s) rotation table of the Givens sweep
+  double *Jb, *Rp, *xs, *zs, *ds, *rs, *us, *cv, *ldiag, *rinv, *Cs, *scr;
+  double2 * grec; // per-link records of the Givens sweep: (t, u) then (c, s) ; (rho, branch) — see givens_recurrence
   int * alist;
-  int * gk;
   int * iscr;
   unsigned short * ilist; // compacted list of the inactive general constraints (constraint scan)
   signed char * stat;
@@ -636,15 +731,12 @@ struct GiCta
     rs = smem + p.off_r;
     us = smem + p.off_u;
     cv = smem + p.off_cv;
-    gc = smem + p.off_gc;
-    gs = smem + p.off_gs;
-    gcs = reinterpret_cast<double2 *>(smem + p.off_gcs);
+    grec = reinterpret_cast<double2 *>(smem + p.off_gcs);
     ldiag = smem + p.off_ldiag;
     rinv = smem + p.off_rinv;
     scr = smem + p.off_scr;
     Cs = smem + p.off_C;
     alist = reinterpret_cast<int *>(smem + p.off_alist);
-    gk = reinterpret_cast<int *>(smem + p.off_gk);
     iscr = reinterpret_cast<int *>(smem + p.off_iscr);
     stat = reinterpret_cast<signed char *>(smem + p.off_stat);
     eqf = reinterpret_cast<signed char *>(smem + p.off_eq);
@@ -1440,7 +1532,7 @@ struct GiCta
   // loads of a row are in flight together (one L2 round trip per round instead of one per chunk), and a round covers
   // 16 NSW inactive constraints — the active ones (60 % at the optimum of config A) cost nothing.
   // ------------------------------------------------------------------------------------------
-  static constexpr int NJ = 8 * W; // chunks of 4 elements per row: n <= 32 W
+  static constexpr int NJB = 8; // chunks of 4 elements in flight per lane (one batch = 32 elements of a row)
 
   template<bool VEC>
   __device__ __forceinline__ double half_dot(const double * ci, const double * xh, const int rem, const int nj, const bool act) const
@@ -1448,36 +1540,42 @@ struct GiCta
     // ci, xh already point at element 2h; this lane owns the elements k' = 4j, 4j+1 < rem of that view.
     // The padding of the x vector (up to npad) is kept at zero, and a missing element is loaded as zero:
     // fma(0, 0, acc) == acc exactly (acc is never -0), so the unconditional FMAs below do not change any bit.
-    double2 v[NJ];
-#pragma unroll
-    for(int j = 0; j < NJ; ++j)
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 1
+    for(int j0 = 0; j0 < nj; j0 += NJB)
     {
-      v[j] = make_double2(0.0, 0.0);
-      if(j < nj && act)
+      double2 v[NJB];
+#pragma unroll
+      for(int u = 0; u < NJB; ++u)
       {
-        if(VEC)
+        const int j = j0 + u;
+        v[u] = make_double2(0.0, 0.0);
+        if(j < nj && act)
         {
-          if(4 * j + 1 < rem)
-            v[j] = *reinterpret_cast<const double2 *>(ci + 4 * j);
-          else if(4 * j < rem)
-            v[j].x = ci[4 * j];
-        }
-        else
-        {
-          if(4 * j < rem) v[j].x = ci[4 * j];
-          if(4 * j + 1 < rem) v[j].y = ci[4 * j + 1];
+          if(VEC)
+          {
+            if(4 * j + 1 < rem)
+              v[u] = *reinterpret_cast<const double2 *>(ci + 4 * j);
+            else if(4 * j < rem)
+              v[u].x = ci[4 * j];
+          }
+          else
+          {
+            if(4 * j < rem) v[u].x = ci[4 * j];
+            if(4 * j + 1 < rem) v[u].y = ci[4 * j + 1];
+          }
         }
       }
-    }
-    double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-    for(int j = 0; j < NJ; ++j)
-    {
-      if(j < nj)
+      for(int u = 0; u < NJB; ++u)
       {
-        const double2 x2 = *reinterpret_cast<const double2 *>(xh + 4 * j);
-        a0 = fma(v[j].x, x2.x, a0);
-        a1 = fma(v[j].y, x2.y, a1);
+        const int j = j0 + u;
+        if(j < nj)
+        {
+          const double2 x2 = *reinterpret_cast<const double2 *>(xh + 4 * j);
+          a0 = fma(v[u].x, x2.x, a0);
+          a1 = fma(v[u].y, x2.y, a1);
+        }
       }
     }
     return a0 + a1;
@@ -1731,12 +1829,6 @@ struct GiCta
       if(c + 1 < n) a1 = fma(Jr[c + 1], ds[c + 1], a1);
       if(c + 2 < n) a2 = fma(Jr[c + 2], ds[c + 2], a2);
       if(j < n) zs[j] = (a0 + a1) + (a2 + a3);
-      // 1 / d[j] for the fall-back branches of the Givens recurrence: one division per thread here, overlapped with
-      // the dot product above, instead of a lane-parallel pass at the head of the recurrence on warp 1
-      if(SPLIT_CHAIN && j >= q && j < n)
-      {
-        reinterpret_cast<double *>(gcs)[j] = 1.0 / ds[j];
-      }
     }
 
     // the two serial recurrences, concurrently on different warps when W > 1
@@ -1759,17 +1851,49 @@ struct GiCta
   __device__ __forceinline__ void back_substitution()
   {
     double w[W], rr[W];
-    bool exact = false;
-#pragma unroll 1
-    for(;;)
-    {
 #pragma unroll
-      for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
-      if(q > 0)
+    for(int s = 0; s < W; ++s) w[s] = lane + 32 * s < q ? ds[lane + 32 * s] : 0.0;
+    if(q > 0)
+    {
+      int k = q - 1;
+      const double * Rk = Rp + colR(k);
+      double wp = ds[k];
+      if(W >= 3)
       {
-        int k = q - 1;
-        const double * Rk = Rp + colR(k);
-        double wp = ds[k];
+        // wide kernels (one CTA per SM, pure latency): the operands of a link are loaded one link ahead (their
+        // addresses do not depend on the recurrence); two links per trip so that no register is copied
+        double rkk = Rk[k], ri = rinv[k];
+        double rnk = Rk[k - 1]; // R(k-1, k); k == 0: an unused read of the word before R
+        double col[W];
+#pragma unroll
+        for(int s = 0; s < W; ++s) col[s] = Rk[lane + 32 * s]; // rows >= k: an unused read past the column
+#pragma unroll 2
+        for(; k >= 0; --k)
+        {
+          const double * Rn = Rk - k; // column k - 1 (k == 0: unused reads around the first column)
+          const double rkk_n = Rn[k - 1], ri_n = rinv[k - 1], rnk_n = Rn[k - 2];
+          double col_n[W];
+#pragma unroll
+          for(int s = 0; s < W; ++s) col_n[s] = Rn[lane + 32 * s];
+          const double wn = __shfl_sync(JRLQP_FULL, pick<W>(w, (k - 1) >> 5), (k - 1) & 31);
+          const double q0 = wp * ri;
+          const double e = fma(-rkk, q0, wp);
+          const double rk = fma(e, ri, q0);
+#pragma unroll
+          for(int s = 0; s < W; ++s)
+            if(lane + 32 * s < k) w[s] = fma(-rk, col[s], w[s]);
+          wp = fma(-rk, rnk, wn);
+          Rk = Rn;
+          rkk = rkk_n;
+          ri = ri_n;
+          rnk = rnk_n;
+#pragma unroll
+          for(int s = 0; s < W; ++s) col[s] = col_n[s];
+        }
+      }
+      else
+      {
+        // narrow kernels (several CTAs per SM, instruction-cache sensitive): the smallest loop body
 #pragma unroll 1
         for(; k >= 0; --k)
         {
@@ -1779,15 +1903,9 @@ struct GiCta
 #pragma unroll
           for(int s = 0; s < W; ++s) col[s] = Rk[lane + 32 * s]; // rows >= k: an unused read past the column
           const double wn = __shfl_sync(JRLQP_FULL, pick<W>(w, (k - 1) >> 5), (k - 1) & 31);
-          double rk;
-          if(!exact)
-          {
-            const double q0 = wp * ri;
-            const double e = fma(-rkk, q0, wp);
-            rk = fma(e, ri, q0);
-          }
-          else
-            rk = wp / rkk;
+          const double q0 = wp * ri;
+          const double e = fma(-rkk, q0, wp);
+          const double rk = fma(e, ri, q0);
 #pragma unroll
           for(int s = 0; s < W; ++s)
             if(lane + 32 * s < k) w[s] = fma(-rk, col[s], w[s]);
@@ -1795,36 +1913,164 @@ struct GiCta
           Rk -= k;
         }
       }
-      bool ok = true;
-#pragma unroll
-      for(int s = 0; s < W; ++s)
-      {
-        const int r = lane + 32 * s;
-        rr[s] = 0.0;
-        if(r < q)
-        {
-          const double y = Rp[colR(r) + r];
-          if(exact)
-            rr[s] = w[s] / y;
-          else
-          {
-            bool okk;
-            rr[s] = div_rcp(w[s], y, rinv[r], okk);
-            ok = ok && okk;
-          }
-        }
-      }
-      if(exact || __all_sync(JRLQP_FULL, ok)) break;
-      exact = true;
     }
+    // every lane redoes the quotient of its own row (same inputs, same bits) and checks the proof
+    bool ok = true;
 #pragma unroll
     for(int s = 0; s < W; ++s)
-      if(lane + 32 * s < q) rs[lane + 32 * s] = rr[s];
+    {
+      const int r = lane + 32 * s;
+      rr[s] = 0.0;
+      if(r < q)
+      {
+        bool okk;
+        rr[s] = div_rcp(w[s], Rp[colR(r) + r], rinv[r], okk);
+        ok = ok && okk;
+      }
+    }
+    if(__all_sync(JRLQP_FULL, ok))
+    {
+#pragma unroll
+      for(int s = 0; s < W; ++s)
+        if(lane + 32 * s < q) rs[lane + 32 * s] = rr[s];
+    }
+    else
+      back_substitution_exact<W>(q, lane, ds, Rp, rs); // a proof was declined: every quotient by the stock division
   }
 
-  // Givens recurrence of the add that may follow (see givens_chain above)
+  // Givens recurrence of the add that may follow: the algorithm of givens_chain above (seeds, 7-operation link,
+  // deferred proofs), with the per-link data in ONE array of 32-byte records so that the loop runs on two pointers
+  // with immediate offsets: grec[2i] = (rs_i, then t_i, then c_i ; ys_i, then u_i, then s_i),
+  // grec[2i+1] = (incoming rho ; branch taken | 8 if the link is to be proven). Every lane stores (same value, same
+  // address): no predicate in the loop.
   static constexpr bool SPLIT_CHAIN = JRLQP_OPT_CS && W > 1;
-  __device__ __forceinline__ void givens_recurrence() { givens_chain<SPLIT_CHAIN>(q, n, lane, ds, gcs, gc, gs, gk, scr, reinterpret_cast<double *>(gcs) + T); }
+  __device__ __forceinline__ static int & rec_kind(double2 & r) { return reinterpret_cast<int *>(&r.y)[0]; }
+  __device__ __forceinline__ void givens_recurrence()
+  {
+    double2 * const rec = grec;
+    // ---- seeds: element j = top - lane of d, chunks of 32 from the last element down; suffix sums by a warp scan
+    {
+      double carry = 0.0;
+#pragma unroll 1
+      for(int top = n - 1; top >= q; top -= 32)
+      {
+        const int j = top - lane;
+        const bool valid = j >= q;
+        const double dj = valid ? ds[j] : 0.0;
+        const double dm = valid ? ds[j - 1] : 0.0; // d of the link this element feeds (j == 0: an unused read of the padding before d)
+        double sc = dj * dj;
+#pragma unroll
+        for(int off = 1; off < 32; off <<= 1)
+        {
+          const double t = __shfl_up_sync(JRLQP_FULL, sc, off);
+          if(lane >= off) sc = sc + t;
+        }
+        const double S = carry + sc;
+        carry = __shfl_sync(JRLQP_FULL, S, 31);
+        double rsd = rsqrt_seed(S);
+        if(j == n - 1) rsd = dj < 0.0 ? -rsd : rsd; // the first rho is d[n-1] itself, sign included
+        const double t = dm * rsd;
+        const double ysd = rsqrt_seed(fma(t, t, 1.0));
+        if(valid)
+        {
+          if(j > q)
+          {
+            rec[2 * (j - 1)] = make_double2(rsd, ysd);
+            rec_kind(rec[2 * (j - 1) + 1]) = 3 | 8;
+          }
+          else
+            scr[11] = rsd; // ~ 1 / rho_q: reciprocal of the new diagonal entry of R (an approximation is all rinv needs)
+        }
+      }
+      __syncwarp();
+    }
+    bool careful = false;
+#pragma unroll 1
+    for(;;)
+    {
+      double rho = ds[n - 1];
+      int i = n - 2;
+      const double * pd = ds + i;
+      double2 * pr = rec + 2 * i;
+      double p = pd[0]; // (n == 1: unused reads of the padding stored before the vectors)
+      double2 sd = pr[0];
+      double q0s = p * sd.x; // first product of the quotient p / rho, issued ahead
+#pragma unroll(W >= 3 ? 2 : 1)
+      for(; i >= q; --i)
+      {
+        // operands of the next link (i == 0: unused reads of the padding)
+        const double pn = pd[-1];
+        const double2 sn = pr[-2];
+        // ---- fast path: t = p / rho, u = sqrt(1 + t^2), r = |rho| u, straight line
+        const double e3 = fma(-rho, q0s, p);
+        double a = fma(e3, sd.x, q0s);
+        const double s = fma(a, a, 1.0);
+        const double g = s * sd.y;
+        const double rem = fma(-g, g, s);
+        const double us = fma(rem, 0.5 * sd.y, g);
+        double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
+        double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
+        const bool slow = careful || !(fabs(p) <= fabs(rho)) || p == 0.0;
+        if(__any_sync(JRLQP_FULL, slow)) // (uniform: every lane holds the same values)
+        {
+          const GivensLink gl = givens_link_slow(p, rho, 0.0, false);
+          a = gl.a;
+          u = gl.u;
+          r = gl.r;
+          rec_kind(pr[1]) = gl.kind;
+        }
+        pr[0] = make_double2(a, u);
+        pr[1].x = rho;
+        rho = r;
+        p = pn;
+        sd = sn;
+        q0s = pn * sn.x;
+        --pd;
+        pr -= 2;
+      }
+      scr[10] = rho;
+      __syncwarp();
+      if(careful) break;
+      // ---- deferred proofs, one link per lane
+      bool ok = true;
+#pragma unroll 1
+      for(int j = q + lane; j <= n - 2; j += 32)
+      {
+        const double2 tu = rec[2 * j];
+        double2 rk = rec[2 * j + 1];
+        if(rec_kind(rk) & 8)
+        {
+          const double a = tu.x, rh = rk.x, us = fabs(tu.y);
+          // t == RN(p / rho) iff |p - rho t| < |rho| ulp(t) / 2, t not a power of two, nothing near underflow
+          const double e2 = fma(-rh, a, ds[j]); // exact remainder
+          const int ahi = __double2hiint(a);
+          const double hu = __hiloint2double((ahi & 0x7ff00000) - 0x03500000, 0);
+          const double tol = fabs(rh) * hu;
+          const bool pow2 = ((ahi & 0xfffff) | __double2loint(a)) == 0;
+          // u == RN(sqrt(s)), s = 1 + t^2 in [1, 2] (so ulp(u) = 2^-52): |s - u^2| < u 2^-52 (1 - 2^-41)
+          const double s = fma(a, a, 1.0);
+          const double rem2 = fma(-us, us, s);
+#ifndef JRLQP_DIAG_NOPROOF
+          ok = ok && fabs(e2) < tol && tol > 1e-270 && !pow2 && fabs(rem2) < us * 0x1.ffffffffffp-53 && us >= 1.0 && us < 2.0;
+#endif
+        }
+      }
+      if(__all_sync(JRLQP_FULL, ok)) break;
+      careful = true;
+    }
+    if(!SPLIT_CHAIN)
+    {
+#pragma unroll 1
+      for(int i = q + lane; i <= n - 2; i += 32) rotation_cs(i);
+    }
+  }
+  // (c, s) of rotation i from what the recurrence stashed (second division of makeGivens), in place
+  __device__ __forceinline__ void rotation_cs(const int i)
+  {
+    const double2 tu = grec[2 * i];
+    double2 rk = grec[2 * i + 1];
+    grec[2 * i] = givens_cs(rec_kind(rk), tu.x, tu.y);
+  }
 
   // ------------------------------------------------------------------------------------------
   // computeStepLength_ (src/GoldfarbIdnaniSolver.cpp:150-219), incl. the activationStatus(k) quirk, in two halves
@@ -1894,7 +2140,7 @@ struct GiCta
     zpos = sqrt(warp_sum32(zz)) > 1e-14;
 
     t2 = P.big_bnd;
-    double cz;
+    double cz, num;
     if(sc.st < ST_LOWER_BOUND)
     {
       // dot4(c, z) and dot4(c, x): accumulator t = sum over k = t, t+4, ... (ascending) is an
@@ -1914,24 +2160,18 @@ struct GiCta
       cz = __shfl_sync(JRLQP_FULL, dot, 0);
       const double cxn = __shfl_sync(JRLQP_FULL, dot, 4);
       nz = sc.st == ST_UPPER ? -cz : cz;
-      if(zpos)
-      {
-        double b = sc.st == ST_UPPER ? bu[sc.p] : bl[sc.p]; // EQUALITY: bl (addInitialConstraint)
-        double cx = cx_valid ? cx_in : cxn;
-        t2 = (b - cx) / cz;
-      }
+      const double b = sc.st == ST_UPPER ? bu[sc.p] : bl[sc.p]; // EQUALITY: bl (addInitialConstraint)
+      num = b - (cx_valid ? cx_in : cxn);
     }
     else
     {
-      int pb = sc.p - mc;
+      const int pb = sc.p - mc;
       cz = zs[pb];
       nz = sc.st == ST_UPPER_BOUND ? -cz : cz;
-      if(zpos)
-      {
-        double b = sc.st == ST_UPPER_BOUND ? xu[pb] : xl[pb];
-        t2 = (b - xs[pb]) / cz;
-      }
+      const double b = sc.st == ST_UPPER_BOUND ? xu[pb] : xl[pb];
+      num = b - xs[pb];
     }
+    if(zpos) t2 = num / cz;
   }
 
   // x += t z ; f += t (n+.z) (t/2 + u[q]) ; u(0:q) -= t r ; u[q] += t   — by warp 0 alone (rows and
@@ -1986,7 +2226,7 @@ struct GiCta
     _Pragma("unroll") for(int u = 0; u < PF; ++u) \
     {                                          \
       X[u] = Jr[(at) - u];                     \
-      Cc[u] = gcs[(at) - u];                   \
+      Cc[u] = grec[2 * ((at) - u)];            \
     }
 #  define JRLQP_ROT_APPLY(X, Cc)                               \
     {                                                          \
@@ -2029,7 +2269,7 @@ struct GiCta
           for(int u = 0; u < PF; ++u)
           {
             xv[u] = Jr[i - u];
-            cv4[u] = gcs[i - u];
+            cv4[u] = grec[2 * (i - u)];
           }
         }
 #pragma unroll 1
@@ -2044,7 +2284,7 @@ struct GiCta
             for(int u = 0; u < PF; ++u)
             {
               xn[u] = Jr[i - PF - u];
-              cn[u] = gcs[i - PF - u];
+              cn[u] = grec[2 * (i - PF - u)];
             }
           }
           double o[PF];
@@ -2072,7 +2312,7 @@ struct GiCta
 #pragma unroll 1
         for(; i >= lo; --i)
         {
-          const double2 cs2 = gcs[i];
+          const double2 cs2 = grec[2 * i];
           const double c = cs2.x, sn = cs2.y;
           const double xi = Jr[i];
           Jr[i + 1] = fma(c, y, sn * xi);
@@ -2416,7 +2656,7 @@ struct GiCta
           {
             // the (c, s) pairs of the sweep, one rotation per thread (second division of makeGivens); published by the
             // barrier below
-            if(tid >= q && tid <= n - 2) gcs[tid] = givens_cs(gk[tid], gc[tid], gs[tid]);
+            if(tid >= q && tid <= n - 2) rotation_cs(tid);
           }
         }
       }
@@ -2460,7 +2700,7 @@ struct GiCta
         }
         if(SPEC && SPLIT_CHAIN)
         {
-          if(tid >= q && tid <= n - 2) gcs[tid] = givens_cs(gk[tid], gc[tid], gs[tid]);
+          if(tid >= q && tid <= n - 2) rotation_cs(tid);
           sync();
         }
         add_constraint();
