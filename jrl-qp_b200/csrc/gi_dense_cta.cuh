@@ -57,6 +57,15 @@ namespace jrlqp
 #ifndef JRLQP_OPT_V2_SCAN
 #  define JRLQP_OPT_V2_SCAN 0
 #endif
+#ifndef JRLQP_BS_PREFETCH
+#  define JRLQP_BS_PREFETCH 3 // back substitution: operands loaded one link ahead (two links per trip) from this many warps per QP on
+#endif
+#ifndef JRLQP_CHAIN_VOTE
+#  define JRLQP_CHAIN_VOTE 1 // Givens recurrence: the branch to the slow link is taken on a warp vote (no convergence barrier on the fast path)
+#endif
+#ifndef JRLQP_CHAIN_UNR
+#  define JRLQP_CHAIN_UNR 1 // links per trip of the Givens recurrence in the narrow kernels (the wide ones always run 2); 2: -3 % at n = 50 (profiles/r02j_ab_A.txt)
+#endif
 #ifndef JRLQP_MINB1
 #  define JRLQP_MINB1 16 // resident CTAs per SM the one-warp kernel is compiled for (register cap 65536 / (32 * MINB1))
 #endif
@@ -716,6 +725,7 @@ struct GiCta
   // ---- solver state (uniform across threads)
   int q;
   double f;
+  bool cv_ready = false; // cv already holds the normal of the next step's constraint (loaded while the rotations were applied)
 #ifdef JRLQP_PHASE_TIMING
   long long ph_t, ph_acc[16];
 #endif
@@ -1770,7 +1780,8 @@ struct GiCta
     const int jc = min(j, n - 1);
     const bool general = sc.st < ST_LOWER_BOUND;
     // stage the selected normal once (coalesced) — it is read by d, c.z and c.x
-    if(general && j < n) cv[j] = Cb[(long long)sc.p * ldC + j];
+    if(general && !cv_ready && j < n) cv[j] = Cb[(long long)sc.p * ldC + j];
+    cv_ready = false;
     sync();
     PH_MARK(2); // fetch of the selected normal
 
@@ -1858,7 +1869,7 @@ struct GiCta
       int k = q - 1;
       const double * Rk = Rp + colR(k);
       double wp = ds[k];
-      if(W >= 3)
+      if(W >= JRLQP_BS_PREFETCH)
       {
         // wide kernels (one CTA per SM, pure latency): the operands of a link are loaded one link ahead (their
         // addresses do not depend on the recurrence); two links per trip so that no register is copied
@@ -1941,9 +1952,11 @@ struct GiCta
   // Givens recurrence of the add that may follow: the algorithm of givens_chain above (seeds, 7-operation link,
   // deferred proofs), with the per-link data in ONE array of 32-byte records so that the loop runs on two pointers
   // with immediate offsets: grec[2i] = (rs_i, then t_i, then c_i ; ys_i, then u_i, then s_i),
-  // grec[2i+1] = (incoming rho ; branch taken | 8 if the link is to be proven). Every lane stores (same value, same
-  // address): no predicate in the loop.
+  // grec[2i+1] = (h_i, then the incoming rho ; branch taken | 8 if the link is to be proven), where the seeds are
+  // rs ~ 1 / rho, g ~ u, h ~ 1 / (2 u). Every lane stores (same value, same address): no predicate in the loop.
   static constexpr bool SPLIT_CHAIN = JRLQP_OPT_CS && W > 1;
+  static constexpr int CHAIN_UNR = W >= 3 ? 2 : JRLQP_CHAIN_UNR;
+  static constexpr bool CHAIN_VOTE = W >= 3 ? false : (JRLQP_CHAIN_VOTE != 0); // measured: profiles/r02j_ab_*.txt
   __device__ __forceinline__ static int & rec_kind(double2 & r) { return reinterpret_cast<int *>(&r.y)[0]; }
   __device__ __forceinline__ void givens_recurrence()
   {
@@ -1970,13 +1983,16 @@ struct GiCta
         double rsd = rsqrt_seed(S);
         if(j == n - 1) rsd = dj < 0.0 ? -rsd : rsd; // the first rho is d[n-1] itself, sign included
         const double t = dm * rsd;
-        const double ysd = rsqrt_seed(fma(t, t, 1.0));
+        const double ss = fma(t, t, 1.0);
+        const double ysd = rsqrt_seed(ss);
         if(valid)
         {
           if(j > q)
           {
-            rec[2 * (j - 1)] = make_double2(rsd, ysd);
-            rec_kind(rec[2 * (j - 1) + 1]) = 3 | 8;
+            rec[2 * (j - 1)] = make_double2(rsd, ss * ysd); // ~ 1 / rho, ~ u = sqrt(1 + t^2)
+            double2 hk = make_double2(0.5 * ysd, 0.0); // ~ 1 / (2 u)
+            rec_kind(hk) = 3 | 8;
+            rec[2 * (j - 1) + 1] = hk;
           }
           else
             scr[11] = rsd; // ~ 1 / rho_q: reciprocal of the new diagonal entry of R (an approximation is all rinv needs)
@@ -1993,25 +2009,27 @@ struct GiCta
       const double * pd = ds + i;
       double2 * pr = rec + 2 * i;
       double p = pd[0]; // (n == 1: unused reads of the padding stored before the vectors)
-      double2 sd = pr[0];
+      double2 sd = pr[0]; // (~ 1 / rho, ~ u)
+      double hh = pr[1].x; // ~ 1 / (2 u)
       double q0s = p * sd.x; // first product of the quotient p / rho, issued ahead
-#pragma unroll(W >= 3 ? 2 : 1)
+#pragma unroll CHAIN_UNR
       for(; i >= q; --i)
       {
         // operands of the next link (i == 0: unused reads of the padding)
         const double pn = pd[-1];
         const double2 sn = pr[-2];
-        // ---- fast path: t = p / rho, u = sqrt(1 + t^2), r = |rho| u, straight line
+        const double hn = pr[-1].x;
+        // ---- fast path, 6 dependent operations: t = p / rho (one correction of p rs), s = 1 + t^2,
+        //      u = sqrt(s) (one correction of the seed: u = g + (s - g^2) / (2 g)), r = |rho| u
         const double e3 = fma(-rho, q0s, p);
         double a = fma(e3, sd.x, q0s);
         const double s = fma(a, a, 1.0);
-        const double g = s * sd.y;
-        const double rem = fma(-g, g, s);
-        const double us = fma(rem, 0.5 * sd.y, g);
+        const double rem = fma(-sd.y, sd.y, s);
+        const double us = fma(rem, hh, sd.y);
         double r = fabs(rho) * us; // == rho * u with u = sign(rho) us, bit for bit
         double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
         const bool slow = careful || !(fabs(p) <= fabs(rho)) || p == 0.0;
-        if(__any_sync(JRLQP_FULL, slow)) // (uniform: every lane holds the same values)
+        if(CHAIN_VOTE ? __any_sync(JRLQP_FULL, slow) : slow) // (uniform: every lane holds the same values)
         {
           const GivensLink gl = givens_link_slow(p, rho, 0.0, false);
           a = gl.a;
@@ -2024,6 +2042,7 @@ struct GiCta
         rho = r;
         p = pn;
         sd = sn;
+        hh = hn;
         q0s = pn * sn.x;
         --pd;
         pr -= 2;
@@ -2439,6 +2458,7 @@ struct GiCta
 
     PH_DECL;
     stage_ct(b);
+    cv_ready = false;
     int it = 0;
     int cursor = 0; // next constraint / bound to test for pre-activation; m when that phase is over
     if(WARM)
@@ -2516,19 +2536,20 @@ struct GiCta
       }
       bool add = false;
       int l = 0;
+      int next_pre = -1; // the next constraint initActiveSet will pre-activate (-1: none left)
       bool scan_now = sel_only; // the scan warps run the scan in this pass
       const double * xv = xs; // ... of this point
       int excl = -1;
       if(!sel_only)
       {
         // will the step after this one need a fresh selection (i.e. is the pre-activation phase over)?
-        bool more_pre = false;
         for(int c = cursor; c < m; ++c)
           if(eqf[c])
           {
-            more_pre = true;
+            next_pre = c;
             break;
           }
+        const bool more_pre = next_pre >= 0;
         const bool want_next = !more_pre && (pre || it + 1 < P.max_iter);
         if(pre || !skip)
         {
@@ -2703,7 +2724,17 @@ struct GiCta
           if(tid >= q && tid <= n - 2) rotation_cs(tid);
           sync();
         }
+        // the normal of the next step's constraint, when it is known already, is fetched while the rotations are applied
+        // (wide kernels only: +4.3 % at n = 128, -1 % at n = 50 where two more registers and the extra code cost more, profiles/r02k_ab_*.txt)
+        const int pnext = W < 3 ? -1 : have_sel ? ((sc.st != ST_INACTIVE && sc.st < ST_LOWER_BOUND) ? sc.p : -1) : (next_pre >= 0 && next_pre < mc ? next_pre : -1);
+        double cvn = 0.0;
+        if(pnext >= 0 && tid < n) cvn = Cb[(long long)pnext * ldC + tid];
         add_constraint();
+        if(pnext >= 0)
+        {
+          if(tid < n) cv[tid] = cvn; // published by the first barrier of compute_step
+          cv_ready = true;
+        }
         PH_MARK(9);
       }
       else
