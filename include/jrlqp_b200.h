@@ -471,6 +471,45 @@ typedef struct jrlqp_blockgi_info
 } jrlqp_blockgi_info;
 int jrlqp_blockgi_get_info(const jrlqp_blockgi * s, jrlqp_blockgi_info * info);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: one handle, one HOST batch, every GPU of the box ("contiguous batch ranges per GPU, one
+ * host thread or stream set per device, host-side scatter/gather; no collective"). The reference solves one QP per
+ * call on one thread (src/GoldfarbIdnaniSolver.cpp:18-54); a caller that loops over a batch of them — the pattern of
+ * benchmarks/Solvers.cpp:513-518 — hands the whole batch to jrlqp_multi_solve_batch_host instead:
+ *   scatter  shard k = instances [lo_k, hi_k) (sizes differ by at most one; jrlqp_multi_shard returns the range) is a
+ *            VIEW of the caller's arrays (pointer + lo_k * stride; arrays shared by the batch, stride 0, go to every
+ *            device once), solved on device k by its own jrlqp_solver — own streams, own device staging — driven by a
+ *            persistent host thread per device;
+ *   gather   every device writes its results straight into the caller's arrays at [lo_k, hi_k): no extra copy.
+ * devices == NULL: devices 0 .. n_devices-1 (n_devices <= 0: all visible). batch_capacity bounds the batch of a call.
+ * Same semantics, statuses and bits as jrlqp_solve_batch_host on one device (tests/test_gpu_multi.py). */
+typedef struct jrlqp_multi jrlqp_multi;
+int jrlqp_multi_create(jrlqp_multi ** out, int32_t n, int32_t mc, int32_t use_bounds, int64_t batch_capacity, const int32_t * devices,
+                       int32_t n_devices);
+int jrlqp_multi_destroy(jrlqp_multi * m);
+int jrlqp_multi_set_options(jrlqp_multi * m, const jrlqp_options * opt);
+int jrlqp_multi_device_count(const jrlqp_multi * m);
+int jrlqp_multi_device(const jrlqp_multi * m, int32_t k); /* CUDA ordinal of shard k */
+jrlqp_solver * jrlqp_multi_solver(jrlqp_multi * m, int32_t k); /* the per-device solver (introspection, tuning switches) */
+/* The range [begin, end) of a batch of `batch` instances that shard k receives in the NEXT call. */
+int jrlqp_multi_shard(const jrlqp_multi * m, int64_t batch, int32_t k, int64_t * begin, int64_t * end);
+/* Load balancing (default on): the shares of the shards start equal (sizes differ by at most one) and then follow the
+ * throughput every device achieved in the previous calls of this handle — the GPUs of one box need not see the same
+ * host-link bandwidth (profiles/r02n_multi_e2e.txt). A share never exceeds 1.5 / n_devices. Results do not depend on
+ * the sharding. on = 0 restores equal shards. jrlqp_multi_get_weights: the current shares (n_devices doubles, sum 1). */
+int jrlqp_multi_set_balancing(jrlqp_multi * m, int32_t on);
+int jrlqp_multi_get_weights(const jrlqp_multi * m, double * weights);
+/* Returns the worst jrlqp_termination_status over the whole batch (>= 0) or a negative JRLQP_ERR_*. */
+int jrlqp_multi_solve_batch_host(jrlqp_multi * m, const jrlqp_problem * pb, const jrlqp_result * res);
+int jrlqp_multi_solve_batch_warm_host(jrlqp_multi * m, const jrlqp_problem * pb, const jrlqp_result * res);
+const char * jrlqp_multi_last_error(const jrlqp_multi * m);
+
+/* Platform probe behind the end-to-end numbers: aggregate GB/s of concurrent pinned-host <-> device copies over
+ * n_devices GPUs (devices == NULL: 0 .. n_devices-1), `bytes` per device and repetition, `reps` repetitions back to
+ * back on one stream per device. direction: 0 host -> device, 1 device -> host, 2 both at once (sum of the two).
+ * per_device (nullable, n_devices entries) receives every device's own GB/s. Negative on error. */
+double jrlqp_measure_host_link(const int32_t * devices, int32_t n_devices, int64_t bytes, int32_t reps, int32_t direction, double * per_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,6 +126,9 @@ EXPORTED_SYMBOLS = [
     "jrlqp_kkt_default_args", "jrlqp_kkt_check_device", "jrlqp_kkt_check_host",
     "jrlqp_blockgi_create", "jrlqp_blockgi_destroy", "jrlqp_blockgi_last_error", "jrlqp_blockgi_set_options",
     "jrlqp_blockgi_get_options", "jrlqp_blockgi_solve_device", "jrlqp_blockgi_solve_host", "jrlqp_blockgi_get_info",
+    "jrlqp_multi_create", "jrlqp_multi_destroy", "jrlqp_multi_set_options", "jrlqp_multi_device_count", "jrlqp_multi_device",
+    "jrlqp_multi_solver", "jrlqp_multi_shard", "jrlqp_multi_solve_batch_host", "jrlqp_multi_solve_batch_warm_host",
+    "jrlqp_multi_last_error", "jrlqp_multi_set_balancing", "jrlqp_multi_get_weights", "jrlqp_measure_host_link",
 ]
 
 _lib = None
@@ -179,8 +182,36 @@ def load_library():
                                                       C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         lib.jrlqp_structured_solve_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                                     C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]
+        lib.jrlqp_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]
+        lib.jrlqp_multi_destroy.argtypes = [C.c_void_p]
+        lib.jrlqp_multi_set_options.argtypes = [C.c_void_p, C.POINTER(_Options)]
+        lib.jrlqp_multi_device_count.argtypes = [C.c_void_p]
+        lib.jrlqp_multi_device.argtypes = [C.c_void_p, C.c_int32]
+        lib.jrlqp_multi_solver.argtypes = [C.c_void_p, C.c_int32]
+        lib.jrlqp_multi_solver.restype = C.c_void_p
+        lib.jrlqp_multi_shard.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.jrlqp_multi_solve_batch_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
+        lib.jrlqp_multi_solve_batch_warm_host.argtypes = [C.c_void_p, C.POINTER(_Problem), C.POINTER(_Result)]
+        lib.jrlqp_multi_set_balancing.argtypes = [C.c_void_p, C.c_int32]
+        lib.jrlqp_multi_get_weights.argtypes = [C.c_void_p, C.c_void_p]
+        lib.jrlqp_multi_last_error.argtypes = [C.c_void_p]
+        lib.jrlqp_multi_last_error.restype = C.c_char_p
+        lib.jrlqp_measure_host_link.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+        lib.jrlqp_measure_host_link.restype = C.c_double
         _lib = lib
     return _lib
+
+
+def measure_host_link(n_devices, nbytes=1 << 30, reps=4, direction=0, devices=None):
+    """Aggregate and per-device GB/s of concurrent pinned-host <-> device copies (jrlqp_measure_host_link):
+    direction 0 host -> device, 1 device -> host, 2 both at once."""
+    lib = load_library()
+    per = (C.c_double * n_devices)()
+    devs = None if devices is None else (C.c_int32 * n_devices)(*devices)
+    agg = lib.jrlqp_measure_host_link(devs, n_devices, nbytes, reps, direction, per)
+    if agg < 0:
+        raise JrlQpError("jrlqp_measure_host_link failed")
+    return float(agg), [float(v) for v in per]
 
 
 def selftest_arith(samples=1 << 24, seed=1, exponent_span=30, rcp_ulps=3, device=0):
@@ -332,17 +363,21 @@ class BatchedGoldfarbIdnaniSolver:
                 if as_in.shape[-1] != m:
                     raise JrlQpError("as_in must have nbCstr + nbBnd entries per instance")
                 pb.as_in, pb.as_stride = _ptr(as_in), (m if as_in.ndim == 2 else 0)
-            fn = self._lib.jrlqp_solve_batch_warm_host
-        else:
-            fn = self._lib.jrlqp_solve_batch_host
-        rc = fn(self._h, C.byref(pb), C.byref(res))
+        rc = self._host_call(pb, res, experimental)
         if rc < 0:
-            raise JrlQpError(f"jrlqp_solve_batch_host failed ({rc}): {self._lib.jrlqp_last_error(self._h).decode()}")
+            raise JrlQpError(f"jrlqp_solve_batch_host failed ({rc}): {self._last_error()}")
         self.last = dict(x=x, u=u, f=f, iterations=it, status=status, active_set=act, active_list=alist,
                          n_active=nact, worst=rc)
         if want_L:
             self.last["L"] = L
         return TerminationStatus(rc)
+
+    def _host_call(self, pb, res, experimental):
+        fn = self._lib.jrlqp_solve_batch_warm_host if experimental else self._lib.jrlqp_solve_batch_host
+        return fn(self._h, C.byref(pb), C.byref(res))
+
+    def _last_error(self):
+        return self._lib.jrlqp_last_error(self._h).decode()
 
     def solve_device(self, B, G, a, Cm, bl, bu, xl, xu, x, u=None, f=None, iterations=None, status=None,
                      active_set=None, active_list=None, n_active=None, L=None, stream=0, shared=(), ldg=None, ldc=None,
@@ -470,6 +505,81 @@ class BatchedGoldfarbIdnaniSolver:
         rc = self._lib.jrlqp_kkt_check_device(C.byref(pb), C.byref(k), self.device, C.c_void_p(stream))
         if rc != 0:
             raise JrlQpError(f"jrlqp_kkt_check_device failed ({rc})")
+
+
+class MultiGpuGoldfarbIdnaniSolver(BatchedGoldfarbIdnaniSolver):
+    """One host batch over every GPU of the box (jrlqp_multi_*, include/jrlqp_b200.h): contiguous shards, one solver
+    and one host thread per device, results written in place — no collective. solve() takes the same
+    HOST arrays as BatchedGoldfarbIdnaniSolver.solve and returns the same outputs, bit for bit."""
+
+    def __init__(self, nbVar, nbCstr, useBounds, batch_capacity=1, devices=None, n_devices=0):
+        self._lib = load_library()
+        self.n, self.mc, self.nb = int(nbVar), int(nbCstr), (int(nbVar) if useBounds else 0)
+        self.m = self.mc + self.nb
+        self.capacity = int(batch_capacity)
+        self._h = None
+        self._mh = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*[int(v) for v in devices])
+            rc = self._lib.jrlqp_multi_create(C.byref(self._mh), self.n, self.mc, int(bool(useBounds)), self.capacity, arr, len(devices))
+        else:
+            rc = self._lib.jrlqp_multi_create(C.byref(self._mh), self.n, self.mc, int(bool(useBounds)), self.capacity, None, int(n_devices))
+        if rc != 0:
+            msg = self._lib.jrlqp_multi_last_error(self._mh).decode() if self._mh else "allocation failed"
+            if self._mh:
+                self._lib.jrlqp_multi_destroy(self._mh)
+                self._mh = None
+            raise JrlQpError(f"jrlqp_multi_create failed ({rc}): {msg}")
+        self.n_devices = int(self._lib.jrlqp_multi_device_count(self._mh))
+        self.devices = [int(self._lib.jrlqp_multi_device(self._mh, k)) for k in range(self.n_devices)]
+        self._h = self._lib.jrlqp_multi_solver(self._mh, 0)  # introspection (kernel_info, host_g_bytes) goes to the first device's solver
+        self._options = SolverOptions()
+        self.last = None
+
+    def __del__(self):
+        mh = getattr(self, "_mh", None)
+        self._h = None
+        if mh:
+            self._lib.jrlqp_multi_destroy(mh)
+            self._mh = None
+
+    def options(self, opt=None):
+        if opt is None:
+            return self._options
+        self._options = opt
+        o = _Options(opt.maxIter_, opt.bigBnd_, int(opt.warmStart_), opt.logFlags_)
+        if self._lib.jrlqp_multi_set_options(self._mh, C.byref(o)) != 0:
+            raise JrlQpError("jrlqp_multi_set_options failed")
+        return self
+
+    def shard(self, batch, k):
+        lo, hi = C.c_int64(), C.c_int64()
+        if self._lib.jrlqp_multi_shard(self._mh, int(batch), int(k), C.byref(lo), C.byref(hi)) != 0:
+            raise JrlQpError("jrlqp_multi_shard failed")
+        return int(lo.value), int(hi.value)
+
+    def set_balancing(self, on):
+        """Shares of the shards follow the measured per-device throughput of the previous calls (default) or stay equal."""
+        if self._lib.jrlqp_multi_set_balancing(self._mh, int(bool(on))) != 0:
+            raise JrlQpError("jrlqp_multi_set_balancing failed")
+        return self
+
+    def weights(self):
+        w = (C.c_double * self.n_devices)()
+        self._lib.jrlqp_multi_get_weights(self._mh, w)
+        return [float(v) for v in w]
+
+    def _host_call(self, pb, res, experimental):
+        fn = self._lib.jrlqp_multi_solve_batch_warm_host if experimental else self._lib.jrlqp_multi_solve_batch_host
+        return fn(self._mh, C.byref(pb), C.byref(res))
+
+    def _last_error(self):
+        return self._lib.jrlqp_multi_last_error(self._mh).decode()
+
+    def solve_device(self, *a, **k):
+        raise JrlQpError("the multi-GPU handle takes host arrays (solve); device pointers belong to one device (BatchedGoldfarbIdnaniSolver)")
+
+    solve_sequence = solve_sequence_device = solve_device
 
 
 class GoldfarbIdnaniSolver:
