@@ -28,7 +28,7 @@ extern "C"
 {
 #endif
 
-#define JRLQP_B200_VERSION 100 /* 0.1.0 */
+#define JRLQP_B200_VERSION 200 /* 0.2.0: multi-GPU entry points, one in-flight device call per handle */
 
 /* include/jrl-qp/enums.h:14-23 — jrl::qp::ActivationStatus (same values, int8 storage) */
 enum jrlqp_activation_status
@@ -151,7 +151,10 @@ int jrlqp_get_options(const jrlqp_solver * s, jrlqp_options * opt);
 
 /* GoldfarbIdnaniSolver::solve (src/GoldfarbIdnaniSolver.cpp:18-54), batched, DEVICE pointers,
  * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
- * Returns JRLQP_OK once enqueued; per-instance statuses land in res->status. */
+ * Returns JRLQP_OK once enqueued; per-instance statuses land in res->status.
+ * One call in flight per HANDLE: a solver owns single-buffered device scratch (as the reference's solver object owns
+ * its workspaces, src/DualSolver.cpp:251-274), so a call enqueued on another stream than the previous one first waits
+ * for it on the device (event). Use one handle per stream for concurrent batches. */
 int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream);
 
 /* Same call with HOST pointers: host->device copies, the kernels, device->host copies, then a

@@ -1,5 +1,6 @@
 // Host side of the structured solver's C-ABI (include/jrlqp_b200.h, jrlqp_blockgi_*): descriptor upload,
 // workspace sizing, the factorisation + solver launches, and the host-pointer entry point. Pure CUDA runtime.
+#include "smem_limit.hpp"
 #include "blockgi.cuh"
 #include "structured_host.hpp"
 
@@ -75,7 +76,7 @@ int configure(jrlqp_blockgi * s)
     s->bthreads = std::max(64, s->g->threads); // measured on config E (profiles/r01za_*): 32 -> 4.2 k, 64 -> 4.6 k, 128 -> 4.4 k, 256 -> 2.3 k QP/s
     if(const char * e = getenv("JRLQP_BLOCKGI_THREADS")) s->bthreads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
   }
-  SCK(cudaFuncSetAttribute(blockgi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
+  SCK(jrlqp::raise_smem_limit(blockgi_kernel, s->smem));
   SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ, blockgi_kernel, s->bthreads, s->smem));
   if(s->occ < 1)
   {

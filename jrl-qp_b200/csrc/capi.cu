@@ -1,6 +1,7 @@
 // Host side of the C-ABI (include/jrlqp_b200.h): solver handle, shared-memory layout, kernel
 // dispatch, and the host-pointer entry point that pipelines H2D copies, the persistent kernel and
 // D2H copies over a few streams. Pure CUDA runtime — no PyTorch, no CPU fallback.
+#include "smem_limit.hpp"
 #include "gi_dense_cta.cuh"
 #include "gi_large.cuh"
 #include "jrlqp_b200.h"
@@ -203,6 +204,11 @@ struct jrlqp_solver
   bool staging_ready = false;
   cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_shared = nullptr;
+  // device entry points: calls on ONE handle are serialised on the device (per-handle scratch — prefactor of a shared G,
+  // transposed shared C, sequence counters — is single-buffered): a call on a different stream first waits for the last one
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
   std::string err;
 
   bool check(cudaError_t e, const char * what)
@@ -234,7 +240,7 @@ static int configure_large(jrlqp_solver * s, bool warm)
     s->err = "large-n kernel: the vectors do not fit in shared memory";
     return JRLQP_ERR_ARG;
   }
-  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(jrlqp::raise_smem_limit(fn, smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kLargeThreads, smem));
   if(occ < 1)
@@ -283,7 +289,7 @@ static int configure_kernel(jrlqp_solver * s)
     fn = pick_kernel(s->warps, stage);
     occ = 0;
     if(smem > s->max_smem_optin) return 0;
-    if(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if(jrlqp::raise_smem_limit(fn, smem) != cudaSuccess)
     {
       cudaGetLastError();
       return 0;
@@ -406,6 +412,7 @@ int jrlqp_destroy(jrlqp_solver * s)
   for(int i = 0; i < kStreams; ++i)
     if(s->streams[i]) cudaStreamDestroy(s->streams[i]);
   if(s->ev_shared) cudaEventDestroy(s->ev_shared);
+  if(s->ev_last) cudaEventDestroy(s->ev_last);
   delete s;
   return JRLQP_OK;
 }
@@ -522,7 +529,7 @@ static int prefactor(jrlqp_solver * s, const jrlqp_problem * pb, cudaStream_t st
   {
     const LargeSmem lay(s->n, s->m, false);
     s->pre_smem = lay.total * 8;
-    CK(cudaFuncSetAttribute(gi_large_prefactor_kernel<kLargeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->pre_smem));
+    CK(jrlqp::raise_smem_limit(gi_large_prefactor_kernel<kLargeThreads>, s->pre_smem));
     CK(cudaMalloc(&s->d_pre, sizeof(double) * (size_t)(3 * n * ldl + 2 * nv)));
     CK(cudaMalloc(&s->d_pre_ok, sizeof(int)));
   }
@@ -731,7 +738,7 @@ static int configure_warm(jrlqp_solver * s)
     s->err = "warm start: problem does not fit in shared memory (n too large; the Householder vectors need n (n - 1) / 2 more doubles)";
     return JRLQP_ERR_ARG;
   }
-  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(jrlqp::raise_smem_limit(fn, smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * s->warps, smem));
   if(occ < 1)
@@ -746,6 +753,22 @@ static int configure_warm(jrlqp_solver * s)
   return JRLQP_OK;
 }
 
+// One in-flight device call per handle: a call enqueued on another stream than the previous one waits for it (event),
+// calls on the same stream are ordered by the stream itself.
+static int serialise_begin(jrlqp_solver * s, cudaStream_t st)
+{
+  if(s->has_last && st != s->last_stream) CK(cudaStreamWaitEvent(st, s->ev_last, 0));
+  return JRLQP_OK;
+}
+static int serialise_end(jrlqp_solver * s, cudaStream_t st)
+{
+  if(!s->ev_last) CK(cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming));
+  CK(cudaEventRecord(s->ev_last, st));
+  s->last_stream = st;
+  s->has_last = true;
+  return JRLQP_OK;
+}
+
 int jrlqp_solve_batch_warm_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream)
 {
   int rc = validate(s, pb, res);
@@ -753,7 +776,10 @@ int jrlqp_solve_batch_warm_device(jrlqp_solver * s, const jrlqp_problem * pb, co
   if(pb->batch == 0) return JRLQP_OK;
   CK(cudaSetDevice(s->device));
   unsigned long long * counter = s->d_counters + (s->next_counter++ % kMaxChunks);
-  return launch(s, pb, res, (cudaStream_t)stream, counter, true);
+  if((rc = serialise_begin(s, (cudaStream_t)stream)) != JRLQP_OK) return rc;
+  rc = launch(s, pb, res, (cudaStream_t)stream, counter, true);
+  if(rc != JRLQP_OK) return rc;
+  return serialise_end(s, (cudaStream_t)stream);
 }
 
 int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result * res, void * stream)
@@ -763,7 +789,10 @@ int jrlqp_solve_batch_device(jrlqp_solver * s, const jrlqp_problem * pb, const j
   if(pb->batch == 0) return JRLQP_OK;
   CK(cudaSetDevice(s->device));
   unsigned long long * counter = s->d_counters + (s->next_counter++ % kMaxChunks);
-  return launch(s, pb, res, (cudaStream_t)stream, counter);
+  if((rc = serialise_begin(s, (cudaStream_t)stream)) != JRLQP_OK) return rc;
+  rc = launch(s, pb, res, (cudaStream_t)stream, counter);
+  if(rc != JRLQP_OK) return rc;
+  return serialise_end(s, (cudaStream_t)stream);
 }
 
 // Device staging of the host entry point. Inputs shared by the whole batch (stride 0) take ONE slot, so a
@@ -1128,7 +1157,10 @@ int jrlqp_solve_sequence_device(jrlqp_solver * s, const jrlqp_problem * pb, cons
   if(rc != JRLQP_OK) return rc;
   if(pb->batch == 0) return JRLQP_OK;
   CK(cudaSetDevice(s->device));
-  return sequence_device_impl(s, pb, seq, res, (cudaStream_t)stream);
+  if((rc = serialise_begin(s, (cudaStream_t)stream)) != JRLQP_OK) return rc;
+  rc = sequence_device_impl(s, pb, seq, res, (cudaStream_t)stream);
+  if(rc != JRLQP_OK) return rc;
+  return serialise_end(s, (cudaStream_t)stream);
 }
 
 int jrlqp_solve_sequence_host(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_sequence * seq, const jrlqp_result * res)

@@ -2520,6 +2520,13 @@ struct GiCta
         }
       }
       bool sel_only = false; // this pass only selects (no selection was made ahead: first iteration without equalities)
+      if(pre && q >= n)
+      {
+        // more than nbVar equalities / fixed variables: the reference would write past its workspaces; the status is
+        // the one its experimental solver returns for the same input
+        write_failure(b, TS_OVERCONSTRAINED_PROBLEM);
+        return;
+      }
       if(!pre)
       {
         if(it >= P.max_iter) break; // MAX_ITER_REACHED

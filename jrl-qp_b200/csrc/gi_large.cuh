@@ -979,6 +979,12 @@ struct GiLarge
           break;
         }
       }
+      if(pre && q >= n)
+      {
+        // more than nbVar equalities / fixed variables (the reference would write past its workspaces)
+        write_failure(b, TS_OVERCONSTRAINED_PROBLEM);
+        return;
+      }
       if(!pre)
       {
         if(it >= P.max_iter) break; // MAX_ITER_REACHED

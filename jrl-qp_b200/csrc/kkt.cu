@@ -66,17 +66,23 @@ __device__ __forceinline__ double dot4_strided(int len, const double * __restric
   return (c0 + c1) + (c2 + c3);
 }
 
+// max that PROPAGATES NaN (fmax drops it): a NaN residual must fail `ndL <= tau_u` as it does in the reference
+__device__ __forceinline__ double max_nan(double a, double b)
+{
+  return a != a ? a : (b != b ? b : fmax(a, b));
+}
+
 template<int T>
 __device__ __forceinline__ double block_max(double v, double * red)
 {
 #pragma unroll
-  for(int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  for(int off = 16; off >= 1; off >>= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, off));
   __syncthreads(); // red may still be read from the previous reduction
   if((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   double r = red[0];
 #pragma unroll
-  for(int w = 1; w < T / 32; ++w) r = fmax(r, red[w]);
+  for(int w = 1; w < T / 32; ++w) r = max_nan(r, red[w]);
   return r;
 }
 
@@ -105,13 +111,13 @@ __global__ void __launch_bounds__(T) kkt_check_kernel(const KktParams p)
     {
       const double v = xb[i];
       xs[i] = v;
-      nx = fmax(nx, fabs(v));
+      nx = max_nan(nx, fabs(v));
     }
     for(int i = tid; i < m; i += T)
     {
       const double v = ub[i];
       us[i] = v;
-      nu = fmax(nu, fabs(v));
+      nu = max_nan(nu, fabs(v));
     }
     nx = block_max<T>(nx, red);
     nu = block_max<T>(nu, red); // its barriers also publish xs / us
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(T) kkt_check_kernel(const KktParams p)
       double t = dot4_strided(n, Gb + i, p.ldg, xs) + ab[i];
       if(nb) t = t + us[mc + i];
       if(mc) t = t + dot4_strided(mc, Cb + i, p.ldc, us);
-      mx = fmax(mx, fabs(t));
+      mx = max_nan(mx, fabs(t));
     }
     const double ndL = block_max<T>(mx, red);
 

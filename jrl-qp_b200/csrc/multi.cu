@@ -346,11 +346,25 @@ static int multi_solve(jrlqp_multi * mh, const jrlqp_problem * pb, const jrlqp_r
     {
       double wsum = 0.0;
       for(double w : mh->weight) wsum += w;
+      for(int k = 0; k < g; ++k) mh->weight[(size_t)k] = 0.5 * mh->weight[(size_t)k] / wsum + 0.5 * rate[(size_t)k] / tot;
+      // shares sum to one and none exceeds 1.5 / g (the capacity of a device): what is cut off goes to the others
       const double cap_share = 1.5 / g;
-      for(int k = 0; k < g; ++k)
+      for(int pass = 0; pass < g; ++pass)
       {
-        const double target = std::min(rate[(size_t)k] / tot, cap_share);
-        mh->weight[(size_t)k] = 0.5 * mh->weight[(size_t)k] / wsum + 0.5 * target;
+        double excess = 0.0, free_sum = 0.0;
+        for(double & w : mh->weight)
+        {
+          if(w > cap_share)
+          {
+            excess += w - cap_share;
+            w = cap_share;
+          }
+          else if(w < cap_share)
+            free_sum += w;
+        }
+        if(excess <= 0.0 || free_sum <= 0.0) break;
+        for(double & w : mh->weight)
+          if(w < cap_share) w += excess * w / free_sum;
       }
     }
   }

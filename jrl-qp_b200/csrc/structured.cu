@@ -1,5 +1,6 @@
 // Host side of the structured-decomposition C-ABI (include/jrlqp_b200.h, jrlqp_structured_*):
 // descriptor upload, launch configuration, and the host-pointer entry points. Pure CUDA runtime.
+#include "smem_limit.hpp"
 #include "structured_host.hpp"
 
 #include <algorithm>
@@ -213,8 +214,8 @@ int jrlqp_structured_create(jrlqp_structured ** out, const jrlqp_structure * st,
     s->err = "structure does not fit in shared memory";
     return JRLQP_ERR_ARG;
   }
-  SCK(cudaFuncSetAttribute(structured_llt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->llt_smem));
-  SCK(cudaFuncSetAttribute(structured_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->solve_smem));
+  SCK(jrlqp::raise_smem_limit(structured_llt_kernel, s->llt_smem));
+  SCK(jrlqp::raise_smem_limit(structured_solve_kernel, s->solve_smem));
   SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->llt_occ, structured_llt_kernel, s->threads, s->llt_smem));
   SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->solve_occ, structured_solve_kernel, s->threads, s->solve_smem));
   if(s->llt_occ < 1 || s->solve_occ < 1)

@@ -131,6 +131,8 @@ EXPORTED_SYMBOLS = [
     "jrlqp_multi_last_error", "jrlqp_multi_set_balancing", "jrlqp_multi_get_weights", "jrlqp_measure_host_link",
 ]
 
+ABI_VERSION = 200  # JRLQP_B200_VERSION of include/jrlqp_b200.h the ctypes structures below were written against
+
 _lib = None
 
 
@@ -145,9 +147,18 @@ def load_library():
     global _lib
     if _lib is None:
         path = library_path()
-        if not os.path.exists(path):
-            _build.build_cuda()
+        if not os.environ.get("JRLQP_B200_LIB"):
+            # incremental (per-object staleness against the sources and the headers they include): a stale binary whose
+            # structures no longer match the ctypes mirrors below is never loaded silently. Without nvcc (a box that
+            # only received the built library) the existing binary is used and checked by its version alone.
+            try:
+                _build.build_cuda()
+            except (OSError, RuntimeError):
+                if not os.path.exists(path):
+                    raise
         lib = C.CDLL(path)
+        if lib.jrlqp_version() != ABI_VERSION:
+            raise ImportError(f"{path}: ABI version {lib.jrlqp_version()}, this package expects {ABI_VERSION} — rebuild (python __graft_entry__.py)")
         lib.jrlqp_launch_count.restype = C.c_int64
         lib.jrlqp_last_error.restype = C.c_char_p
         lib.jrlqp_last_error.argtypes = [C.c_void_p]
@@ -346,6 +357,18 @@ class BatchedGoldfarbIdnaniSolver:
         B = max(Bs) if Bs else 1
         if mc == 0:
             Cm = bl = bu = None
+        # sizes are checked here, as the reference's asserts do (src/GoldfarbIdnaniSolver.cpp:33-39): a mis-shaped array
+        # would otherwise be read out of bounds by the copies
+        want = {"G": (n, n), "a": (n,), "C": (mc, n), "bl": (mc,), "bu": (mc,), "xl": (n,), "xu": (n,)}
+        for k, v in (("G", G), ("a", a), ("C", Cm), ("bl", bl), ("bu", bu), ("xl", xl), ("xu", xu)):
+            if v is None:
+                if k in ("G", "a") or (k in ("C", "bl", "bu") and mc) or (k in ("xl", "xu") and self.nb):
+                    raise JrlQpError(f"INCONSISTENT_INPUT: {k} is missing")
+                continue
+            if tuple(v.shape[-len(want[k]):]) != want[k] or (k not in shared and v.shape[0] != B) or v.ndim not in (full[k], full[k] - 1):
+                raise JrlQpError(f"INCONSISTENT_INPUT: {k} has shape {v.shape}, expected {('B',) + want[k]} (or {want[k]} shared) with B = {B}")
+        if B > self.capacity:
+            raise JrlQpError(f"batch {B} exceeds the capacity {self.capacity} given at construction")
         x = np.empty((B, n))
         u = np.empty((B, m))
         f = np.empty(B)

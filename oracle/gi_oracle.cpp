@@ -235,7 +235,7 @@ TerminationStatus GIOracle::solve(double * G,
   // set (src/GoldfarbIdnaniSolver.cpp:75), so warmStart is ignored here, as in the reference.
   needExpand_ = true;
   it_ = 0;
-  if(!init()) return NON_POS_HESSIAN;
+  if(!init()) return overconstrained_ ? OVERCONSTRAINED_PROBLEM : NON_POS_HESSIAN;
   return mainLoop();
 }
 
@@ -371,19 +371,39 @@ bool GIOracle::init()
 
   A_.reset(); // src/GoldfarbIdnaniSolver.cpp:75
   initActiveSet(); // :79
-  return true;
+  return !overconstrained_;
 }
 
 void GIOracle::initActiveSet()
 {
-  // src/GoldfarbIdnaniSolver.cpp:268-287
+  // src/GoldfarbIdnaniSolver.cpp:268-287. The reference pre-activates without looking at the count: with more than
+  // nbVar equalities / fixed variables it writes past its workspaces (undefined behaviour). Here — and in the CUDA
+  // kernels — the (nbVar + 1)-th pre-activation ends the solve with OVERCONSTRAINED_PROBLEM, the status the
+  // experimental solver returns for the same input (src/experimental/GoldfarbIdnaniSolver.cpp:360-362).
+  overconstrained_ = false;
   for(int i = 0; i < A_.nbCstr(); ++i)
   {
-    if(bl_[i] == bu_[i]) addInitialConstraint({i, EQUALITY});
+    if(bl_[i] == bu_[i])
+    {
+      if(A_.nbActiveCstr() >= n_)
+      {
+        overconstrained_ = true;
+        return;
+      }
+      addInitialConstraint({i, EQUALITY});
+    }
   }
   for(int i = 0; i < A_.nbBnd(); ++i)
   {
-    if(xl_[i] == xu_[i]) addInitialConstraint({A_.nbCstr() + i, FIXED});
+    if(xl_[i] == xu_[i])
+    {
+      if(A_.nbActiveCstr() >= n_)
+      {
+        overconstrained_ = true;
+        return;
+      }
+      addInitialConstraint({A_.nbCstr() + i, FIXED});
+    }
   }
 }
 

@@ -203,6 +203,7 @@ private:
     ActivationStatus st = INACTIVE;
   };
   bool init();
+  bool overconstrained_ = false; // more than nbVar equalities / fixed variables met by initActiveSet
   void initActiveSet();
   void addInitialConstraint(Selected sc);
   Selected select();

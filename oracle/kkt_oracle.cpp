@@ -21,6 +21,11 @@
 using gi_oracle::dot32;
 using gi_oracle::dot4;
 
+static inline double max_nan(double a, double b)
+{
+  return a != a ? a : (b != b ? b : (a < b ? b : a));
+}
+
 namespace
 {
 // src/test/kkt.cpp:14-23
@@ -88,8 +93,9 @@ int kkt_oracle_check_batch(int n,
       const double * xb = x + b * n;
       const double * ub = u + b * m;
       double nx = 0, nu = 0;
-      for(int i = 0; i < n; ++i) nx = std::max(nx, std::abs(xb[i]));
-      for(int i = 0; i < m; ++i) nu = std::max(nu, std::abs(ub[i]));
+      // (NaN-propagating maxima: a NaN solution must fail the `<= tau` tests, as it does in the reference)
+      for(int i = 0; i < n; ++i) nx = max_nan(nx, std::abs(xb[i]));
+      for(int i = 0; i < m; ++i) nu = max_nan(nu, std::abs(ub[i]));
       const double tau_x = tau_p * (1 + nx);
       const double tau_u = tau_d * (1 + nu);
       // stationarity
@@ -99,7 +105,7 @@ int kkt_oracle_check_batch(int n,
         double t = dot4(n, Gb + i, ldg, xb, 1) + ab[i];
         if(nb) t = t + ub[mc + i];
         if(mc) t = t + dot4(mc, Cb + i, ldc, ub, 1);
-        ndL = std::max(ndL, std::abs(t));
+        ndL = max_nan(ndL, std::abs(t));
       }
       int fl = 0;
       if(ndL <= tau_u) fl |= 1;

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert set(S.EXPORTED_SYMBOLS) <= declared
     for name in sorted(declared):
         assert hasattr(lib, name), f"libjrlqp_b200.so does not export {name}"
-    assert lib.jrlqp_version() == 100
+    assert lib.jrlqp_version() == S.ABI_VERSION
 
 
 def test_struct_mirrors_match_header_sizes():
