@@ -392,6 +392,11 @@ typedef struct jrlqp_structured_info
   int32_t num_sms;
   int64_t elements_per_instance; /* doubles of the factor actually touched (algorithmic bytes / 8) */
 } jrlqp_structured_info;
+/* Kernel used by jrlqp_structured_llt_*: 0 automatic, 1 the general kernel (one CTA per instance, tiles in shared memory),
+ * 2 the small-tile kernel (tri-block-diagonal chains of uniform dense 8 / 12 / 16-row tiles: two instances per warp, tiles in
+ * registers), 3 the same with the tiles of the next block fetched by TMA bulk copies (cp.async.bulk + mbarrier). All
+ * produce the same bits. Environment override at creation: JRLQP_STRUCT_KERNEL. */
+int jrlqp_structured_set_kernel(jrlqp_structured * s, int32_t mode);
 int jrlqp_structured_get_info(const jrlqp_structured * s, jrlqp_structured_info * info);
 
 /* ---------------------------------------------------------------------------------------------

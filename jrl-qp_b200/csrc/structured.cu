@@ -2,13 +2,20 @@
 // descriptor upload, launch configuration, and the host-pointer entry points. Pure CUDA runtime.
 #include "smem_limit.hpp"
 #include "structured_host.hpp"
+#include "structured_small.cuh"
 
 #include <algorithm>
+#include <cstdint>
+#include <cstdlib>
 #include <atomic>
 #include <string>
 #include <vector>
 
 using namespace jrlqp;
+
+#ifndef JRLQP_STRUCT_DEFAULT_SMALL
+#  define JRLQP_STRUCT_DEFAULT_SMALL 3 // automatic mode on an eligible structure: 2 = small tiles (plain loads), 3 = small tiles + TMA
+#endif
 
 namespace jrlqp
 {
@@ -230,6 +237,27 @@ int jrlqp_structured_create(jrlqp_structured ** out, const jrlqp_structure * st,
   SCK(upload(s->d_doff, s->doff));
   SCK(upload(s->d_ooff, s->ooff));
   SCK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  // eligibility for the small-tile kernel
+  {
+    const int nb = s->size[0];
+    bool okk = s->type == SG_TRI && (nb == 8 || nb == 12 || nb == 16);
+    for(int i = 0; i < s->b && okk; ++i) okk = s->size[i] == nb && s->dld[i] == nb && (s->doff[i] % 2) == 0;
+    for(int i = 0; i + 1 < s->b && okk; ++i) okk = s->old[i] == nb && (s->ooff[i] % 2) == 0;
+    s->small_nb = okk ? nb : 0;
+    if(const char * e = getenv("JRLQP_STRUCT_KERNEL")) s->kernel_mode = atoi(e);
+  }
+  return JRLQP_OK;
+}
+
+int jrlqp_structured_set_kernel(jrlqp_structured * s, int32_t mode)
+{
+  if(!s || mode < 0 || mode > 3) return JRLQP_ERR_ARG;
+  if(mode >= 2 && s->small_nb == 0)
+  {
+    s->err = "the small-tile kernel needs a tri-block-diagonal chain of uniform dense tiles of 8, 12 or 16 rows";
+    return JRLQP_ERR_ARG;
+  }
+  s->kernel_mode = mode;
   return JRLQP_OK;
 }
 
@@ -274,6 +302,28 @@ int jrlqp_structured_llt_device(jrlqp_structured * s, double * data, int64_t str
   p.stride = stride;
   p.batch = batch;
   p.ok = ok;
+  // small uniform tiles: two instances per warp, tiles in registers (structured_small.cuh); needs 16-byte aligned instances
+  const bool aligned = (reinterpret_cast<uintptr_t>(data) % 16) == 0 && (stride % 2) == 0;
+  const int mode = s->kernel_mode == 0 ? (s->small_nb && aligned ? JRLQP_STRUCT_DEFAULT_SMALL : 1) : s->kernel_mode;
+  if(mode >= 2 && s->small_nb && aligned)
+  {
+    const bool tma = mode == 3;
+    const int nb = s->small_nb, tt = nb * nb;
+    const int smem = 4 * (2 * tt + (tma ? 8 * tt + 2 : 0)) * 8;
+    void (*fn)(const StructParams) = nullptr;
+    if(nb == 8) fn = tma ? structured_llt_small_kernel<8, true> : structured_llt_small_kernel<8, false>;
+    if(nb == 12) fn = tma ? structured_llt_small_kernel<12, true> : structured_llt_small_kernel<12, false>;
+    if(nb == 16) fn = tma ? structured_llt_small_kernel<16, true> : structured_llt_small_kernel<16, false>;
+    SCK(jrlqp::raise_smem_limit(fn, smem));
+    int occ = 0;
+    SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, smem));
+    const long long pairs = (batch + 1) / 2;
+    const long long grid = std::min<long long>((pairs + 3) / 4, (long long)std::max(occ, 1) * s->num_sms);
+    fn<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(p);
+    count_launch();
+    SCK(cudaGetLastError());
+    return JRLQP_OK;
+  }
   const long long grid = std::min<long long>(batch, (long long)s->llt_occ * s->num_sms);
   structured_llt_kernel<<<(unsigned)grid, s->threads, s->llt_smem, (cudaStream_t)stream>>>(p);
   count_launch();

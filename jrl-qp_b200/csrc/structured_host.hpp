@@ -22,6 +22,10 @@ struct jrlqp_structured
   std::vector<int> size, dld, old, start;
   std::vector<long long> doff, ooff;
   long long min_stride = 0; // one past the last element any block touches
+  // small-tile kernel (structured_small.cuh): tile size if the structure is a tri-block-diagonal chain of uniform dense
+  // tiles of 8, 12 or 16 rows at even offsets, else 0; kernel_mode: 0 automatic, 1 general, 2 small tiles, 3 small tiles + TMA
+  int small_nb = 0;
+  int kernel_mode = 0;
   // device copies of the descriptor
   int *d_size = nullptr, *d_dld = nullptr, *d_old = nullptr, *d_start = nullptr;
   long long *d_doff = nullptr, *d_ooff = nullptr;

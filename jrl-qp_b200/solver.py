@@ -120,7 +120,7 @@ EXPORTED_SYMBOLS = [
     "jrlqp_set_stage_c", "jrlqp_launch_count", "jrlqp_last_error", "jrlqp_measure_fp64_tflops",
     "jrlqp_structured_create", "jrlqp_structured_destroy", "jrlqp_structured_last_error",
     "jrlqp_structured_llt_device", "jrlqp_structured_llt_host", "jrlqp_structured_solve_device",
-    "jrlqp_structured_solve_host", "jrlqp_structured_get_info", "jrlqp_selftest_arith",
+    "jrlqp_structured_solve_host", "jrlqp_structured_get_info", "jrlqp_structured_set_kernel", "jrlqp_selftest_arith",
     "jrlqp_solve_batch_warm_device", "jrlqp_solve_batch_warm_host", "jrlqp_set_kernel_path", "jrlqp_set_scan_transposed", "jrlqp_host_g_bytes",
     "jrlqp_solve_sequence_device", "jrlqp_solve_sequence_host",
     "jrlqp_kkt_default_args", "jrlqp_kkt_check_device", "jrlqp_kkt_check_host",

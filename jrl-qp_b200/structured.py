@@ -187,6 +187,13 @@ class StructuredG:
     def nbVar(self, i=None):
         return self.st.n if i is None else int(self.st.sizes[i])
 
+    def set_kernel(self, mode):
+        """jrlqp_structured_set_kernel: 0 automatic, 1 general kernel, 2 small-tile kernel, 3 small-tile kernel + TMA."""
+        self._lib.jrlqp_structured_set_kernel.argtypes = [C.c_void_p, C.c_int32]
+        if self._lib.jrlqp_structured_set_kernel(self._h, int(mode)) != 0:
+            raise RuntimeError(self._lib.jrlqp_structured_last_error(self._h).decode())
+        return self
+
     def lltInPlace(self):
         """bool per instance (the reference returns false when a diagonal block is not positive definite)."""
         rc = self._lib.jrlqp_structured_llt_host(self._h, self.data.ctypes.data_as(C.c_void_p), C.c_int64(self.st.stride),

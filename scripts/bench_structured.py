@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--kernel", type=int, default=0, help="jrlqp_structured_set_kernel: 0 automatic, 1 general, 2 small tiles, 3 small tiles + TMA")
     args = ap.parse_args()
     type = {"tri": Type.TriBlockDiagonal, "down": Type.BlockArrowDown, "up": Type.BlockArrowUp}[args.type]
     sizes = [args.size] * args.blocks
@@ -49,6 +50,8 @@ def main():
     v = v0.clone()
     g = StructuredG(st, base[:1].copy())  # handle only; device pointers are passed explicitly below
     lib, h = S.load_library(), g._h
+    if args.kernel:
+        assert lib.jrlqp_structured_set_kernel(h, args.kernel) == 0, lib.jrlqp_structured_last_error(h)
     stream = torch.cuda.current_stream()
 
     def llt():
@@ -118,7 +121,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_llt, "higher_is_better": True, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"config E: {args.type} structure, {args.blocks} blocks of {args.size}x{args.size}, batch {B}",
-                   "layout": "packed tiles", "kernel": {"threads": inf.threads, "llt_smem": inf.llt_smem, "llt_ctas_per_sm": inf.llt_occ,
+                   "layout": "packed tiles", "llt_kernel_mode": args.kernel, "kernel": {"threads": inf.threads, "llt_smem": inf.llt_smem, "llt_ctas_per_sm": inf.llt_occ,
                                                         "solve_smem": inf.solve_smem, "solve_ctas_per_sm": inf.solve_occ}},
         "roofline": {"bound": "hbm", "achieved": bytes_llt * B / t_llt / 1e9, "peak": hbm, "unit": "GB/s",
                      "frac": bytes_llt * B / t_llt / 1e9 / hbm, "traffic": None, "bytes_per_instance": bytes_llt,

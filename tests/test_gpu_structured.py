@@ -21,10 +21,12 @@ pytestmark = pytest.mark.gpu
 ALL_TYPES = [Type.TriBlockDiagonal, Type.BlockArrowDown, Type.BlockArrowUp]
 
 
-def _factor_both(st, H):
+def _factor_both(st, H, kernel=0):
     data_ref = st.pack(H)
     ok_ref = po.decomp_llt(st, data_ref, nthreads=os.cpu_count())
     g = StructuredG(st, st.pack(H))
+    if kernel:
+        g.set_kernel(kernel)
     before = S.launch_count()
     ok = g.lltInPlace()
     assert S.launch_count() > before, "no CUDA kernel was launched"
@@ -124,3 +126,39 @@ def test_dense_layout_keeps_upper_triangle():
     a, b = g.data.reshape(4, 13, 13), data0.reshape(4, 13, 13)
     iu = np.triu_indices(13, 1)
     assert np.array_equal(a[:, iu[1], iu[0]], b[:, iu[1], iu[0]])  # [col][row] storage: strict upper untouched
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("size,blocks,batch", [(12, 32, 1001), (8, 5, 77), (16, 3, 130), (12, 1, 9), (12, 2, 1)])
+def test_small_tile_llt_kernels_bit_exact(kernel, size, blocks, batch):
+    """The general kernel (1), the small-tile kernel (2: two instances per warp, tiles in registers) and its TMA
+    variant (3: next tiles by cp.async.bulk + mbarrier) produce the bits of the oracle — odd batches (a warp with one
+    live instance), a single block, and instances that are NOT positive definite (nothing written from the failing
+    block on, the other instance of the warp unaffected)."""
+    sizes = [size] * blocks
+    st = Structure.packed(Type.TriBlockDiagonal, sizes)
+    H = sc.make_H(Type.TriBlockDiagonal, sizes, batch, seed=5 + size, shift=1.0)
+    bad = sorted({b for b in (0, 3, batch - 1) if b < batch})
+    for j, b in enumerate(bad):
+        blk = min(blocks - 1, j)  # break a different diagonal block in each of them
+        k = blk * size + size // 2
+        H[b, k, k] = -abs(H[b, k, k])
+    g, ok, data_ref, ok_ref = _factor_both(st, H, kernel)
+    assert np.array_equal(ok, ok_ref.astype(bool))
+    assert not ok[bad].any() and ok.sum() == batch - len(bad)
+    good = ok.astype(bool)
+    # (a failed instance holds a partially overwritten block in the reference — Eigen's llt_inplace works in place — and
+    # the untouched input here: its contents are unspecified, only the flag is compared)
+    assert np.array_equal(g.data[good], data_ref[good]), "factor not bit-identical to the oracle"
+    # the solves (general kernel) consume the factor left by any of the three
+    rng = np.random.default_rng(0)
+    V = rng.uniform(-1, 1, (batch, 1, st.n))
+    ref = po.decomp_solve(st, data_ref, V.copy(), transpose=False, nthreads=os.cpu_count())
+    assert np.array_equal(g.solveL(V.copy())[good], ref[good])
+
+
+def test_small_tile_kernel_refused_on_other_structures():
+    st = Structure.packed(Type.BlockArrowDown, [12] * 4)
+    g = StructuredG(st, st.pack(sc.make_H(Type.BlockArrowDown, [12] * 4, 2, seed=1, shift=1.0)))
+    with pytest.raises(RuntimeError):
+        g.set_kernel(2)
