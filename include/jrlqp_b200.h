@@ -220,6 +220,14 @@ int jrlqp_version(void);
  * TFLOP/s (2 flops per FMA), or a negative error. Used by bench.py for the roofline denominator. */
 double jrlqp_measure_fp64_tflops(int32_t device, int32_t repeats);
 
+/* FP64 tensor-core experiment (jrl-qp_b200/csrc/dmma_probe.cu): a 128 x 128 x 64 product per 4-warp CTA, one CTA per SM
+ * (the shape and residency of the n = 128 solver kernel), `reps` times. out6 (HOST): [0] GFLOP/s of a register-blocked
+ * FP64-pipe kernel, [1] GFLOP/s of an mma.sync.m8n8k4.f64 (DMMA) kernel, [2] fraction of single-DMMA outputs equal to the
+ * sequential fma chain over k, [3] ... equal to the pairwise order, [4] fraction of length-64 inner products evaluated by
+ * DMMA with the canonical dot4 interleaving that equal dot4 bit for bit, [5] fraction of outputs on which the two product
+ * kernels agree bit for bit. */
+int jrlqp_probe_dmma(int32_t device, int32_t reps, double * out6);
+
 /* Self-test of the short-latency exact division / square root used on the solver's serial
  * recurrences (jrl-qp_b200/csrc/fp64_exact.cuh) against the stock IEEE operations, on `samples`
  * pseudo-random operand pairs with binary exponents in [-exponent_span, exponent_span] and a

@@ -66,6 +66,11 @@ namespace jrlqp
 #ifndef JRLQP_CHAIN_UNR
 #  define JRLQP_CHAIN_UNR 1 // links per trip of the Givens recurrence in the narrow kernels (the wide ones always run 2); 2: -3 % at n = 50 (profiles/r02j_ab_A.txt)
 #endif
+#ifndef JRLQP_BULK_PREFETCH
+#  define JRLQP_BULK_PREFETCH 0 // 1: ticket look-ahead, the next problem's G and C pulled into L2 by TMA bulk prefetches (cp.async.bulk.prefetch.L2)
+                                // while the current one is solved. Measured (profiles/r02u_ab_*.txt): -0.4 % at n = 50 and n = 128, -2.8 % at n = 20 — the
+                                // staging loads are not what these kernels wait for (long_scoreboard 4 % of the stall samples): off
+#endif
 #ifndef JRLQP_MINB1
 #  define JRLQP_MINB1 16 // resident CTAs per SM the one-warp kernel is compiled for (register cap 65536 / (32 * MINB1))
 #endif
@@ -823,7 +828,7 @@ struct GiCta
       for(int c = 0; c < mc; ++c)
         if(i < n) Cs[c * P.ldcs + i] = __ldg(Cg + i + (long long)c * P.ldc);
     }
-    else if(mc > 0 && Ct == nullptr)
+    else if(!JRLQP_BULK_PREFETCH && mc > 0 && Ct == nullptr)
     {
       // pull this problem's C towards L2 while the factorisation runs (it is first needed by the scan)
       const char * Cg = reinterpret_cast<const char *>(P.C + b * P.sC);
@@ -2847,6 +2852,38 @@ __global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W
     cta.Ct = p.ct + (long long)ct_slot * p.ct_stride;
     cta.sync();
   }
+#if JRLQP_BULK_PREFETCH
+  // Ticket look-ahead: the index of the NEXT problem is drawn before the current one is solved, and its matrices are
+  // pulled towards L2 by the TMA engine (one bulk prefetch per array: no register, no load instruction per line), so
+  // that the staging loads of the next init() find them there instead of waiting on HBM.
+  if(threadIdx.x == 0) *ticket = atomicAdd(p.counter, 1ull);
+  cta.sync();
+  unsigned long long b = *ticket;
+  cta.sync();
+  while(b < (unsigned long long)p.batch)
+  {
+    if(threadIdx.x == 0)
+    {
+      const unsigned long long nb = atomicAdd(p.counter, 1ull);
+      *ticket = nb;
+      if(nb < (unsigned long long)p.batch)
+      {
+        auto bulk = [](const double * ptr, long long doubles)
+        {
+          const unsigned bytes = (unsigned)(doubles * 8);
+          if((reinterpret_cast<unsigned long long>(ptr) & 15ull) == 0ull && (bytes & 15u) == 0u && bytes > 0u)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+        };
+        if(p.sG != 0) bulk(p.G + nb * p.sG, (long long)(p.n - 1) * p.ldg + p.n);
+        if(p.sC != 0 && p.mc > 0) bulk(p.C + nb * p.sC, (long long)(p.mc - 1) * p.ldc + p.n);
+      }
+    }
+    cta.solve((long long)b);
+    cta.sync();
+    b = *ticket;
+    cta.sync();
+  }
+#else
   for(;;)
   {
     if(threadIdx.x == 0) *ticket = atomicAdd(p.counter, 1ull);
@@ -2856,6 +2893,7 @@ __global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W
     cta.solve((long long)b);
     cta.sync();
   }
+#endif
   if(ct_slot >= 0 && threadIdx.x == 0)
   {
     __threadfence();

@@ -128,11 +128,12 @@ EXPORTED_SYMBOLS = [
     "jrlqp_blockgi_get_options", "jrlqp_blockgi_solve_device", "jrlqp_blockgi_solve_host", "jrlqp_blockgi_get_info",
     "jrlqp_multi_create", "jrlqp_multi_destroy", "jrlqp_multi_set_options", "jrlqp_multi_device_count", "jrlqp_multi_device",
     "jrlqp_multi_solver", "jrlqp_multi_shard", "jrlqp_multi_solve_batch_host", "jrlqp_multi_solve_batch_warm_host",
-    "jrlqp_multi_last_error", "jrlqp_multi_set_balancing", "jrlqp_multi_get_weights", "jrlqp_measure_host_link",
+    "jrlqp_probe_dmma", "jrlqp_multi_last_error", "jrlqp_multi_set_balancing", "jrlqp_multi_get_weights", "jrlqp_measure_host_link",
 ]
 
 ABI_VERSION = 200  # JRLQP_B200_VERSION of include/jrlqp_b200.h the ctypes structures below were written against
 
+_check_abi = True  # scripts/ab_variants.py loads older variant builds (same structures) on purpose
 _lib = None
 
 
@@ -157,7 +158,7 @@ def load_library():
                 if not os.path.exists(path):
                     raise
         lib = C.CDLL(path)
-        if lib.jrlqp_version() != ABI_VERSION:
+        if _check_abi and lib.jrlqp_version() != ABI_VERSION:
             raise ImportError(f"{path}: ABI version {lib.jrlqp_version()}, this package expects {ABI_VERSION} — rebuild (python __graft_entry__.py)")
         lib.jrlqp_launch_count.restype = C.c_int64
         lib.jrlqp_last_error.restype = C.c_char_p
@@ -223,6 +224,17 @@ def measure_host_link(n_devices, nbytes=1 << 30, reps=4, direction=0, devices=No
     if agg < 0:
         raise JrlQpError("jrlqp_measure_host_link failed")
     return float(agg), [float(v) for v in per]
+
+
+def probe_dmma(device=0, reps=64):
+    """jrlqp_probe_dmma: dict of the six figures of the FP64 tensor-core experiment."""
+    out = (C.c_double * 6)()
+    rc = load_library().jrlqp_probe_dmma(C.c_int32(device), C.c_int32(reps), out)
+    if rc != 0:
+        raise JrlQpError(f"jrlqp_probe_dmma failed ({rc})")
+    keys = ("fp64_pipe_gflops", "dmma_gflops", "dmma_equals_sequential_fma_chain", "dmma_equals_pairwise_order",
+            "dmma_dot4_interleaving_equals_dot4", "pipe_and_dmma_products_agree")
+    return dict(zip(keys, [float(v) for v in out]))
 
 
 def selftest_arith(samples=1 << 24, seed=1, exponent_span=30, rcp_ulps=3, device=0):

@@ -21,6 +21,10 @@ SOURCES = ["gi_oracle.cpp", "gi_oracle_capi.cpp", "decomp_oracle.cpp", "decomp_o
 HEADERS = ["gi_oracle.hpp", "decomp_oracle.hpp", "warm_oracle.hpp", "block_oracle.hpp"]
 BASE_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-pthread", "-DNDEBUG", "-Wall", "-Wextra"]
 VARIANTS = {"fma": ["-mfma", "-mavx2"], "generic": []}
+# A third build of the SAME sources for timing only (bench.py cpu_baseline.fast_port): -O3, AVX2 + FMA, and the compiler
+# free to contract, reassociate and vectorise (-ffast-math): NOT bit-pinned, never used as a checker. It brackets what an
+# optimised Eigen build of the reference could reach on the same cores beside the bit-pinned port.
+FAST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-ffast-math", "-mfma", "-mavx2", "-funroll-loops", "-pthread", "-DNDEBUG"]
 
 
 def _srcs():
@@ -62,10 +66,24 @@ def build(force=False, verbose=False):
     return paths
 
 
+def build_fast(force=False, verbose=False):
+    """The timing-only variant (see FAST_FLAGS). Returns its path, or None on a host without AVX2 + FMA."""
+    if not cpu_has_fma():
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    target = os.path.join(OUT, "liboracle_fast.so")
+    if force or _stale(target):
+        cmd = ["g++"] + FAST_FLAGS + _srcs() + ["-o", target]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+    return target
+
+
 def library_path():
     paths = build()
     return paths["fma"] if cpu_has_fma() else paths["generic"]
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True), build_fast(force="--force" in sys.argv, verbose=True))

@@ -50,8 +50,22 @@ def _stride(a, per):
     return 0 if a is None or a.size == per else per
 
 
+_fast = None
+
+
+def fast_lib():
+    """The timing-only build (-O3 -ffast-math, AVX2 + FMA: NOT bit-pinned, see build.py) or None."""
+    global _fast
+    if _fast is None:
+        path = _build.build_fast()
+        if path is None:
+            return None
+        _fast = C.CDLL(path)
+    return _fast
+
+
 def solve_batch(G, a, Cm, bl, bu, xl=None, xu=None, max_iter=500, big_bnd=1e100, nthreads=1,
-                want_L=False, instrument=False, experimental=False, warm_start=False, as_in=None):
+                want_L=False, instrument=False, experimental=False, warm_start=False, as_in=None, fast=False):
     """G: [B,n,n] (each n x n block column-major, i.e. G[b, j, i] = G_b(i, j); symmetric input makes
     this immaterial), a: [B,n], Cm: [B,mc,n] (row i = constraint normal i = column i of the reference's
     n x mc column-major C), bl/bu: [B,mc], xl/xu: [B,n] or None. Arrays with one dimension less are
@@ -89,10 +103,11 @@ def solve_batch(G, a, Cm, bl, bu, xl=None, xu=None, max_iter=500, big_bnd=1e100,
         Cm = np.zeros((1,))
         bl = np.zeros((1,))
         bu = np.zeros((1,))
-    fn = lib().gi_oracle_solve_batch
+    L_ = fast_lib() if fast else lib()  # fast: timing only, results are NOT the canonical bits
+    fn = L_.gi_oracle_solve_batch
     pre = []
     if experimental:
-        fn = lib().gi_oracle_solve_batch_warm
+        fn = L_.gi_oracle_solve_batch_warm
         if as_in is not None:
             as_in = np.ascontiguousarray(as_in, dtype=np.int8)
             assert as_in.shape[-1] == m

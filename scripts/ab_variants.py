@@ -30,6 +30,7 @@ def main():
     d = {k: torch.from_numpy(getattr(pb, k)).to(dev) for k in ("G", "a", "C", "bl", "bu", "xl", "xu")}
     Bn, n, m = pb.batch, pb.n, pb.mc + pb.n
     solvers, outs = {}, {}
+    S._check_abi = False
     for name in args.names:
         path = os.path.join(B.OUT, "libjrlqp_b200.so" if name == "main" else f"libjrlqp_b200_{name}.so")
         S._lib = None

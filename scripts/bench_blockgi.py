@@ -26,7 +26,7 @@ from jrl_qp_b200.blockgi import BatchedBlockGISolver  # noqa: E402
 from jrl_qp_b200.structured import Type  # noqa: E402
 
 
-def main():
+def main(argv=None, emit=True):
     ap = argparse.ArgumentParser()
     ap.add_argument("--type", default="tri", choices=["tri", "down", "up"])
     ap.add_argument("--blocks", type=int, default=32)
@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--dense-sample", type=int, default=2048)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     import block_cases as bc
     import pyoracle as po
     type = {"tri": Type.TriBlockDiagonal, "down": Type.BlockArrowDown, "up": Type.BlockArrowUp}[args.type]
@@ -154,7 +154,9 @@ def main():
         "gpu_launches": int(launches),
         "verified": {"all_success": all_ok, "planted_solution": planted, "oracle_bit_exact_sample": parity, "mean_iterations": mean_it},
     }
-    print(json.dumps(line))
+    if emit:
+        print(json.dumps(line))
+    return line
 
 
 if __name__ == "__main__":

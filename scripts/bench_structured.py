@@ -23,7 +23,7 @@ from jrl_qp_b200 import solver as S  # noqa: E402
 from jrl_qp_b200.structured import Structure, StructuredG, Type, _CStructure  # noqa: E402
 
 
-def main():
+def main(argv=None, emit=True):
     ap = argparse.ArgumentParser()
     ap.add_argument("--type", default="tri", choices=["tri", "down", "up"])
     ap.add_argument("--blocks", type=int, default=32)
@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--kernel", type=int, default=0, help="jrlqp_structured_set_kernel: 0 automatic, 1 general, 2 small tiles, 3 small tiles + TMA")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     type = {"tri": Type.TriBlockDiagonal, "down": Type.BlockArrowDown, "up": Type.BlockArrowUp}[args.type]
     sizes = [args.size] * args.blocks
     st = Structure.packed(type, sizes)
@@ -131,7 +131,9 @@ def main():
         "cpu_baseline": {"value": cs / t_cpu, "unit": "instances/s", "cores": cores, "kind": "port", "sample": f"first {cs} instances"},
         "verified": {"oracle_bit_exact_sample": parity, "llt_reconstructs_H": fact_ok},
     }
-    print(json.dumps(line))
+    if emit:
+        print(json.dumps(line))
+    return line
 
 
 if __name__ == "__main__":
