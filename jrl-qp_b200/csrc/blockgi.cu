@@ -73,7 +73,7 @@ int configure(jrlqp_blockgi * s)
   s->smem = (int)smem;
   if(s->bthreads == 0)
   {
-    s->bthreads = std::max(64, s->g->threads); // measured on config E (profiles/r01za_*): 32 -> 4.2 k, 64 -> 4.6 k, 128 -> 4.4 k, 256 -> 2.3 k QP/s
+    s->bthreads = std::max(128, s->g->threads); // the Householder records are applied by the whole CTA over 128 classes (blockgi.cuh)
     if(const char * e = getenv("JRLQP_BLOCKGI_THREADS")) s->bthreads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
   }
   SCK(jrlqp::raise_smem_limit(blockgi_kernel, s->smem));

@@ -113,7 +113,7 @@ struct BlockGi
   const int n, mc, m, T, tid, lane, warp, W;
   const bool up;
   // shared memory
-  double *x, *z, *d, *w, *u, *r, *scr, *Lt, *Bt;
+  double *x, *z, *d, *w, *u, *r, *scr, *hred, *Lt, *Bt;
   int *rec, *alist, *iscr;
   signed char * st;
   // per problem
@@ -135,7 +135,8 @@ struct BlockGi
     u = w + ne;
     r = u + ne;
     scr = r + ne;
-    Lt = scr + 80;
+    hred = scr + 80; // 128 class sums + the scaled dot of a Householder application
+    Lt = hred + 136;
     Bt = Lt + p.G.nmax * p.G.nmax;
     rec = reinterpret_cast<int *>(Bt + p.G.nmax * p.G.nmax);
     alist = rec + 3 * p.max_iter;
@@ -149,7 +150,7 @@ struct BlockGi
   static __host__ __device__ long long smem_bytes(int n, int nmax, int m, int max_iter)
   {
     const long long ne = (n + 2) & ~1;
-    return (6 * ne + 80 + 2LL * nmax * nmax) * 8 + (3LL * max_iter + n + 16) * 4 + ((m + 15) & ~15);
+    return (6 * ne + 80 + 136 + 2LL * nmax * nmax) * 8 + (3LL * max_iter + n + 16) * 4 + ((m + 15) & ~15);
   }
 
   __device__ __forceinline__ int pidx(int i) const { return up ? sg_perm(P.G, i) : i; }
@@ -215,30 +216,47 @@ struct BlockGi
     }
   }
 
-  // ---- OrthonormalSequence::applyTransposeToTheLeft / applyToTheLeft on a vector in shared memory: warp 0 only
+  // ---- OrthonormalSequence::applyTransposeToTheLeft / applyToTheLeft on a vector in shared memory.
+  // One Householder record = a reflector of up to n entries stored in the CTA's global slice (L2): applied by the WHOLE
+  // CTA. The inner product E.w runs over 128 classes (k mod 128, ascending k in each: thread t owns the classes t, t + T,
+  // ...), which are folded (c, c+32), (c+64, c+96) and then reduced by the dot32 butterfly — the order the oracle
+  // defines (oracle/block_oracle.hpp); every entry of the reflector is loaded once, all loads of a record in flight
+  // together. Round 1 applied a record with one warp: 12 dependent L2 round trips per pass at n = 384, two passes per
+  // record, ~100 records, twice per iteration — 95 % of a solve (profiles/r01zc_blockgi_E_tri.json: 4.8 k QP/s).
   __device__ __forceinline__ void householder(const double * p, int len, double * v)
   {
     const double tau = p[0];
-    double acc = 0;
-    for(int k = lane; k < len; k += 32) acc = fma(k == 0 ? 1.0 : p[k], v[k], acc);
-    for(int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(BG_FULL, acc, off);
-    const double hd = tau * acc;
-    for(int k = lane; k < len; k += 32) v[k] = fma(-hd, k == 0 ? 1.0 : p[k], v[k]);
-    __syncwarp();
+    for(int c = tid; c < 128; c += T)
+    {
+      double acc = 0.0;
+      for(int k = c; k < len; k += 128) acc = fma(k == 0 ? 1.0 : p[k], v[k], acc);
+      hred[c] = acc;
+    }
+    __syncthreads();
+    if(warp == 0)
+    {
+      double acc = (hred[lane] + hred[lane + 32]) + (hred[lane + 64] + hred[lane + 96]);
+      for(int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(BG_FULL, acc, off);
+      if(lane == 0) hred[128] = tau * acc;
+    }
+    __syncthreads();
+    const double hd = hred[128];
+    for(int k = tid; k < len; k += T) v[k] = fma(-hd, k == 0 ? 1.0 : p[k], v[k]);
+    __syncthreads();
   }
 
   __device__ void apply_qt(double * v)
   {
-    if(warp == 0)
+    for(int e = 0; e < nrec; ++e)
     {
-      for(int e = 0; e < nrec; ++e)
+      const int start = rec[3 * e], size = rec[3 * e + 1];
+      const double * p = Qg + rec[3 * e + 2];
+      double * vs = v + (start & 0x7fffffff);
+      if(start >= 0)
+        householder(p, size, vs);
+      else
       {
-        const int start = rec[3 * e], size = rec[3 * e + 1];
-        const double * p = Qg + rec[3 * e + 2];
-        double * vs = v + (start & 0x7fffffff);
-        if(start >= 0)
-          householder(p, size, vs);
-        else
+        if(warp == 0)
         {
           // Givens(c, s)^T, i ascending: x' = c x - s y, y' = s x + c y; the y' of one rotation is the x of the next
           double carry = vs[0];
@@ -257,8 +275,8 @@ struct BlockGi
             }
           }
           if(lane == 0) vs[size] = carry;
-          __syncwarp();
         }
+        __syncthreads();
       }
     }
     __syncthreads();
@@ -266,16 +284,16 @@ struct BlockGi
 
   __device__ void apply_q(double * v)
   {
-    if(warp == 0)
+    for(int e = nrec - 1; e >= 0; --e)
     {
-      for(int e = nrec - 1; e >= 0; --e)
+      const int start = rec[3 * e], size = rec[3 * e + 1];
+      const double * p = Qg + rec[3 * e + 2];
+      double * vs = v + (start & 0x7fffffff);
+      if(start >= 0)
+        householder(p, size, vs);
+      else
       {
-        const int start = rec[3 * e], size = rec[3 * e + 1];
-        const double * p = Qg + rec[3 * e + 2];
-        double * vs = v + (start & 0x7fffffff);
-        if(start >= 0)
-          householder(p, size, vs);
-        else
+        if(warp == 0)
         {
           // Givens(c, s), i descending: x' = c x + s y, y' = -s x + c y; the x' of one rotation is the y of the next
           double carry = vs[size];
@@ -295,8 +313,8 @@ struct BlockGi
             }
           }
           if(lane == 0) vs[0] = carry;
-          __syncwarp();
         }
+        __syncthreads();
       }
     }
     __syncthreads();

@@ -212,10 +212,13 @@ void BlockGIOracle::applyQt(double * v) const
     {
       // size_ == 1 Householder branch (:104-108): d = E.dot(w); w -= h d E, E = [1; essential]
       const double tau = p[0];
+      // E.w over 128 classes (k mod 128, ascending k), folded (c, c+32), (c+64, c+96), then the dot32 butterfly
+      double a128[128];
+      for(int l = 0; l < 128; ++l) a128[l] = 0;
+      a128[0] = std::fma(1.0, w[0], a128[0]);
+      for(int k = 1; k < h.size; ++k) a128[k & 127] = std::fma(p[k], w[k], a128[k & 127]);
       double acc[32];
-      for(int l = 0; l < 32; ++l) acc[l] = 0;
-      acc[0] = std::fma(1.0, w[0], acc[0]);
-      for(int k = 1; k < h.size; ++k) acc[k & 31] = std::fma(p[k], w[k], acc[k & 31]);
+      for(int l = 0; l < 32; ++l) acc[l] = (a128[l] + a128[l + 32]) + (a128[l + 64] + a128[l + 96]);
       for(int off = 16; off >= 1; off >>= 1)
       {
         double nxt[32];
@@ -252,10 +255,13 @@ void BlockGIOracle::applyQ(double * v) const
     if(h.type == 0)
     {
       const double tau = p[0];
+      // E.w over 128 classes (k mod 128, ascending k), folded (c, c+32), (c+64, c+96), then the dot32 butterfly
+      double a128[128];
+      for(int l = 0; l < 128; ++l) a128[l] = 0;
+      a128[0] = std::fma(1.0, w[0], a128[0]);
+      for(int k = 1; k < h.size; ++k) a128[k & 127] = std::fma(p[k], w[k], a128[k & 127]);
       double acc[32];
-      for(int l = 0; l < 32; ++l) acc[l] = 0;
-      acc[0] = std::fma(1.0, w[0], acc[0]);
-      for(int k = 1; k < h.size; ++k) acc[k & 31] = std::fma(p[k], w[k], acc[k & 31]);
+      for(int l = 0; l < 32; ++l) acc[l] = (a128[l] + a128[l + 32]) + (a128[l + 64] + a128[l + 96]);
       for(int off = 16; off >= 1; off >>= 1)
       {
         double nxt[32];

@@ -36,7 +36,8 @@
 //   structured factorisation / solves   decomp_oracle.hpp
 //   cx_j = C_b(:,j) . x_b               dot4 over the rows of the block that holds constraint j
 //   Householder H = I - tau e e^T, e = [1; essential], applied to a segment w (both directions):
-//                                       s = dot32(e, w); w_i = fma(-(tau s), e_i, w_i)
+//                                       s = dot128(e, w) (128 accumulators k mod 128, ascending k; folded (c + c+32) + (c+64 + c+96)
+//                                       to 32, then the dot32 butterfly); w_i = fma(-(tau s), e_i, w_i)
 //   Givens sequence, Q^T direction      i ascending:  (x, y) = (w_i, w_i+1): x' = fma(c,x,-(s y)); y' = fma(c,y,s x)
 //   Givens sequence, Q direction        i descending: x' = fma(c,x,s y); y' = fma(c,y,-(s x))
 //   makeHouseholder(d_tail)             tailSq = dot32(tail, tail); if tailSq <= DBL_MIN: tau = 0, beta = c0,
