@@ -487,6 +487,14 @@ typedef struct jrlqp_blockgi_info
 } jrlqp_blockgi_info;
 int jrlqp_blockgi_get_info(const jrlqp_blockgi * s, jrlqp_blockgi_info * info);
 
+/* Test harness of internal::OrthonormalSequence as the structured solver stores it (tests/InternalTest.cpp:35-323): the
+ * kernel's own applyToTheLeft (transpose = 0) / applyTransposeToTheLeft (1) on `ncases` HOST vectors v [ncases][n], in
+ * place. rec: nrec triples (start, size, offset into qdata); Householder record: start >= 0, `size` entries
+ * [tau, essential(size-1)] — H = I - tau e e^T, e = [1; essential] embedded at `start`; Givens record: start | 0x80000000,
+ * `size` rotations on the rows (start + i, start + i + 1), data [c(size), s(size)]. */
+int jrlqp_blockgi_test_sequence(int32_t device, int32_t n, int32_t nrec, const int32_t * rec, const double * qdata, int64_t qlen, double * v,
+                                int32_t ncases, int32_t transpose, int32_t threads);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Multi-GPU: one handle, one HOST batch, every GPU of the box ("contiguous batch ranges per GPU, one
  * host thread or stream set per device, host-side scatter/gather; no collective"). The reference solves one QP per

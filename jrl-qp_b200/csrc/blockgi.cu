@@ -74,7 +74,7 @@ int configure(jrlqp_blockgi * s)
   if(s->bthreads == 0)
   {
     s->bthreads = std::max(128, s->g->threads); // the Householder records are applied by the whole CTA over 128 classes (blockgi.cuh)
-    if(const char * e = getenv("JRLQP_BLOCKGI_THREADS")) s->bthreads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
+    if(const char * e = getenv("JRLQP_BLOCKGI_THREADS")) s->bthreads = std::max(128, std::min(1024, atoi(e) / 32 * 32)); // (>= 128: one class of the reflector products per thread)
   }
   SCK(jrlqp::raise_smem_limit(blockgi_kernel, s->smem));
   SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ, blockgi_kernel, s->bthreads, s->smem));
@@ -400,3 +400,48 @@ int jrlqp_blockgi_solve_host(jrlqp_blockgi * s, const jrlqp_block_problem * pb, 
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Test harness of the orthonormal sequence (include/jrlqp_b200.h: jrlqp_blockgi_test_sequence)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int jrlqp_blockgi_test_sequence(int32_t device, int32_t n, int32_t nrec, const int32_t * rec, const double * qdata, int64_t qlen,
+                                           double * v, int32_t ncases, int32_t transpose, int32_t threads)
+{
+  if(n < 2 || nrec < 0 || !rec || !qdata || !v || ncases < 1 || threads < 128 || threads % 32 != 0 || threads > 1024 || n > 1024) return JRLQP_ERR_ARG;
+  if(cudaSetDevice(device) != cudaSuccess) return JRLQP_ERR_CUDA;
+  const long long rsz = (long long)n * (n + 1) / 2;
+  double *d_ws = nullptr, *d_v = nullptr;
+  int * d_rec = nullptr;
+  bool ok = cudaMalloc(&d_ws, sizeof(double) * (rsz + qlen + 1)) == cudaSuccess && cudaMalloc(&d_v, sizeof(double) * (size_t)n * ncases) == cudaSuccess &&
+            cudaMalloc(&d_rec, sizeof(int) * (3 * (size_t)nrec + 1)) == cudaSuccess;
+  ok = ok && cudaMemcpy(d_ws + rsz, qdata, sizeof(double) * qlen, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(d_v, v, sizeof(double) * (size_t)n * ncases, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(d_rec, rec, sizeof(int) * 3 * (size_t)nrec, cudaMemcpyHostToDevice) == cudaSuccess;
+  int rc = JRLQP_ERR_CUDA;
+  if(ok)
+  {
+    BlockGiParams p{};
+    p.G.n = n;
+    p.G.nmax = 1;
+    p.G.type = SG_TRI;
+    p.mc = 0;
+    p.nb = 0;
+    p.max_iter = std::max(nrec, 1);
+    p.ws = d_ws;
+    p.ws_stride = 0;
+    p.qcap = qlen;
+    const int smem = (int)BlockGi::smem_bytes(n, 1, 0, p.max_iter);
+    ok = jrlqp::raise_smem_limit(blockgi_sequence_test_kernel, smem) == cudaSuccess;
+    if(ok)
+    {
+      blockgi_sequence_test_kernel<<<1, threads, smem>>>(p, d_rec, nrec, d_v, ncases, transpose);
+      count_launch();
+      ok = cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(v, d_v, sizeof(double) * (size_t)n * ncases, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    rc = ok ? JRLQP_OK : JRLQP_ERR_CUDA;
+  }
+  cudaFree(d_ws);
+  cudaFree(d_v);
+  cudaFree(d_rec);
+  return rc;
+}

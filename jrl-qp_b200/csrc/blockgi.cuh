@@ -223,14 +223,49 @@ struct BlockGi
   // defines (oracle/block_oracle.hpp); every entry of the reflector is loaded once, all loads of a record in flight
   // together. Round 1 applied a record with one warp: 12 dependent L2 round trips per pass at n = 384, two passes per
   // record, ~100 records, twice per iteration — 95 % of a solve (profiles/r01zc_blockgi_E_tri.json: 4.8 k QP/s).
-  __device__ __forceinline__ void householder(const double * p, int len, double * v)
+  static constexpr int MAXE = 8; // entries of a reflector per thread: 128 classes x 8 >= n (n <= 1024)
+
+  // entries k = tid, tid + 128, ... of the reflector of record e (1.0 for the implicit leading entry), and its tau:
+  // loaded one record AHEAD of their use, so that the L2 / HBM latency of a record hides behind the reduction of the
+  // previous one (the record list of a config-E solve does not fit L2: ncu, profiles/r02y_*: L2 hit rate 21 %, the dot
+  // of the reflector 19 % of the stall samples, all long_scoreboard)
+  __device__ __forceinline__ void load_reflector(int e, double (&pk)[MAXE], double & tau) const
   {
-    const double tau = p[0];
-    for(int c = tid; c < 128; c += T)
+    const int start = rec[3 * e], size = rec[3 * e + 1];
+    const double * p = Qg + rec[3 * e + 2];
+    tau = 0.0;
+#pragma unroll
+    for(int j = 0; j < MAXE; ++j) pk[j] = 0.0;
+    if(start >= 0)
+    {
+      tau = p[0];
+      if(tid < 128)
+      {
+#pragma unroll
+        for(int j = 0; j < MAXE; ++j)
+        {
+          const int k = tid + 128 * j;
+          if(k < size) pk[j] = k == 0 ? 1.0 : p[k];
+        }
+      }
+    }
+  }
+
+  // H = I - tau E E^T applied to v(0:len), E held in registers (load_reflector). The inner product E.w runs over 128
+  // classes (k mod 128, ascending k in each), folded (c, c+32), (c+64, c+96) and reduced by the dot32 butterfly: the order
+  // the oracle defines (oracle/block_oracle.hpp).
+  __device__ __forceinline__ void householder(const double (&pk)[MAXE], double tau, int len, double * v)
+  {
+    if(tid < 128)
     {
       double acc = 0.0;
-      for(int k = c; k < len; k += 128) acc = fma(k == 0 ? 1.0 : p[k], v[k], acc);
-      hred[c] = acc;
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = tid + 128 * j;
+        if(k < len) acc = fma(pk[j], v[k], acc);
+      }
+      hred[tid] = acc;
     }
     __syncthreads();
     if(warp == 0)
@@ -241,84 +276,92 @@ struct BlockGi
     }
     __syncthreads();
     const double hd = hred[128];
-    for(int k = tid; k < len; k += T) v[k] = fma(-hd, k == 0 ? 1.0 : p[k], v[k]);
-    __syncthreads();
-  }
-
-  __device__ void apply_qt(double * v)
-  {
-    for(int e = 0; e < nrec; ++e)
+    if(tid < 128)
     {
-      const int start = rec[3 * e], size = rec[3 * e + 1];
-      const double * p = Qg + rec[3 * e + 2];
-      double * vs = v + (start & 0x7fffffff);
-      if(start >= 0)
-        householder(p, size, vs);
-      else
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
       {
-        if(warp == 0)
-        {
-          // Givens(c, s)^T, i ascending: x' = c x - s y, y' = s x + c y; the y' of one rotation is the x of the next
-          double carry = vs[0];
-          for(int i0 = 0; i0 < size; i0 += 32)
-          {
-            const int k = min(i0 + lane, size - 1);
-            const double cl = p[k], sl = p[size + k];
-            const int cnt = min(32, size - i0);
-            for(int j = 0; j < cnt; ++j)
-            {
-              const double c = __shfl_sync(BG_FULL, cl, j), s = __shfl_sync(BG_FULL, sl, j);
-              const double xi = carry, yi = vs[i0 + j + 1];
-              const double nx = fma(c, xi, -(s * yi));
-              carry = fma(c, yi, s * xi);
-              if(lane == 0) vs[i0 + j] = nx;
-            }
-          }
-          if(lane == 0) vs[size] = carry;
-        }
-        __syncthreads();
+        const int k = tid + 128 * j;
+        if(k < len) v[k] = fma(-hd, pk[j], v[k]);
       }
     }
     __syncthreads();
   }
 
-  __device__ void apply_q(double * v)
+  // dir = +1: Q^T v (records in order of addition), dir = -1: Q v (reverse order)
+  __device__ void apply_sequence(double * v, const int dir)
   {
-    for(int e = nrec - 1; e >= 0; --e)
+    if(nrec > 0)
     {
-      const int start = rec[3 * e], size = rec[3 * e + 1];
-      const double * p = Qg + rec[3 * e + 2];
-      double * vs = v + (start & 0x7fffffff);
-      if(start >= 0)
-        householder(p, size, vs);
-      else
+      double pc[MAXE], pn[MAXE], tc, tn = 0.0;
+      int e = dir > 0 ? 0 : nrec - 1;
+      load_reflector(e, pc, tc);
+      for(int cnt = 0; cnt < nrec; ++cnt, e += dir)
       {
-        if(warp == 0)
+        const int en = e + dir;
+        if(cnt + 1 < nrec) load_reflector(en, pn, tn);
+        const int start = rec[3 * e], size = rec[3 * e + 1];
+        double * vs = v + (start & 0x7fffffff);
+        if(start >= 0)
+          householder(pc, tc, size, vs);
+        else
         {
-          // Givens(c, s), i descending: x' = c x + s y, y' = -s x + c y; the x' of one rotation is the y of the next
-          double carry = vs[size];
-          for(int i1 = size; i1 > 0; i1 -= 32)
+          const double * p = Qg + rec[3 * e + 2];
+          if(warp == 0)
           {
-            const int cnt = min(32, i1);
-            const int k = max(i1 - 1 - lane, 0);
-            const double cl = p[k], sl = p[size + k];
-            for(int j = 0; j < cnt; ++j)
+            if(dir > 0)
             {
-              const int i = i1 - 1 - j;
-              const double c = __shfl_sync(BG_FULL, cl, j), s = __shfl_sync(BG_FULL, sl, j);
-              const double xi = vs[i], yi = carry;
-              carry = fma(c, xi, s * yi);
-              const double ny = fma(c, yi, -(s * xi));
-              if(lane == 0) vs[i + 1] = ny;
+              // Givens(c, s)^T, i ascending: x' = c x - s y, y' = s x + c y; the y' of one rotation is the x of the next
+              double carry = vs[0];
+              for(int i0 = 0; i0 < size; i0 += 32)
+              {
+                const int k = min(i0 + lane, size - 1);
+                const double cl = p[k], sl = p[size + k];
+                const int cn = min(32, size - i0);
+                for(int j = 0; j < cn; ++j)
+                {
+                  const double c = __shfl_sync(BG_FULL, cl, j), sn = __shfl_sync(BG_FULL, sl, j);
+                  const double xi = carry, yi = vs[i0 + j + 1];
+                  const double nx = fma(c, xi, -(sn * yi));
+                  carry = fma(c, yi, sn * xi);
+                  if(lane == 0) vs[i0 + j] = nx;
+                }
+              }
+              if(lane == 0) vs[size] = carry;
+            }
+            else
+            {
+              // Givens(c, s), i descending: x' = c x + s y, y' = -s x + c y; the x' of one rotation is the y of the next
+              double carry = vs[size];
+              for(int i1 = size; i1 > 0; i1 -= 32)
+              {
+                const int cn = min(32, i1);
+                const int k = max(i1 - 1 - lane, 0);
+                const double cl = p[k], sl = p[size + k];
+                for(int j = 0; j < cn; ++j)
+                {
+                  const int i = i1 - 1 - j;
+                  const double c = __shfl_sync(BG_FULL, cl, j), sn = __shfl_sync(BG_FULL, sl, j);
+                  const double xi = vs[i], yi = carry;
+                  carry = fma(c, xi, sn * yi);
+                  const double ny = fma(c, yi, -(sn * xi));
+                  if(lane == 0) vs[i + 1] = ny;
+                }
+              }
+              if(lane == 0) vs[0] = carry;
             }
           }
-          if(lane == 0) vs[0] = carry;
+          __syncthreads();
         }
-        __syncthreads();
+#pragma unroll
+        for(int j = 0; j < MAXE; ++j) pc[j] = pn[j];
+        tc = tn;
       }
     }
     __syncthreads();
   }
+  __device__ void apply_qt(double * v) { apply_sequence(v, +1); }
+  __device__ void apply_q(double * v) { apply_sequence(v, -1); }
 
   // ---- selectViolatedConstraint_ (src/experimental/BlockGISolver.cpp:111-164)
   __device__ __forceinline__ void slacks(int i, double & sl, double & su) const
@@ -777,6 +820,28 @@ __global__ void blockgi_kernel(const BlockGiParams P)
     const long long b = next;
     if(b >= P.batch) break;
     S.solve(b);
+  }
+}
+
+// Test harness (tests/test_orthonormal_sequence.py; tests/InternalTest.cpp:35-323 of the reference): the solver's OWN
+// apply_q / apply_qt run on a record list given by the caller — records in the layout add_constraint / remove_constraint
+// write (rec = (start | sign bit for Givens, size, offset), data in the Q slice of the workspace) — on `ncases` vectors.
+__global__ void blockgi_sequence_test_kernel(const BlockGiParams P, const int * rec_in, int nrec, double * v, int ncases, int transpose)
+{
+  extern __shared__ __align__(16) double sm[];
+  BlockGi S(P, sm);
+  for(int i = threadIdx.x; i < 3 * nrec; i += blockDim.x) S.rec[i] = rec_in[i];
+  S.nrec = nrec;
+  for(int cs = blockIdx.x; cs < ncases; cs += gridDim.x)
+  {
+    __syncthreads();
+    for(int i = threadIdx.x; i < S.n; i += blockDim.x) S.w[i] = v[(long long)cs * S.n + i];
+    __syncthreads();
+    if(transpose)
+      S.apply_qt(S.w);
+    else
+      S.apply_q(S.w);
+    for(int i = threadIdx.x; i < S.n; i += blockDim.x) v[(long long)cs * S.n + i] = S.w[i];
   }
 }
 

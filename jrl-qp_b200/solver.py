@@ -128,7 +128,7 @@ EXPORTED_SYMBOLS = [
     "jrlqp_blockgi_get_options", "jrlqp_blockgi_solve_device", "jrlqp_blockgi_solve_host", "jrlqp_blockgi_get_info",
     "jrlqp_multi_create", "jrlqp_multi_destroy", "jrlqp_multi_set_options", "jrlqp_multi_device_count", "jrlqp_multi_device",
     "jrlqp_multi_solver", "jrlqp_multi_shard", "jrlqp_multi_solve_batch_host", "jrlqp_multi_solve_batch_warm_host",
-    "jrlqp_probe_dmma", "jrlqp_multi_last_error", "jrlqp_multi_set_balancing", "jrlqp_multi_get_weights", "jrlqp_measure_host_link",
+    "jrlqp_blockgi_test_sequence", "jrlqp_probe_dmma", "jrlqp_multi_last_error", "jrlqp_multi_set_balancing", "jrlqp_multi_get_weights", "jrlqp_measure_host_link",
 ]
 
 ABI_VERSION = 200  # JRLQP_B200_VERSION of include/jrlqp_b200.h the ctypes structures below were written against

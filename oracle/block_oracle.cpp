@@ -500,6 +500,58 @@ const double * BlockGIOracle::multipliers()
   return uExp_.data();
 }
 
+
+// ---- test hooks (see block_oracle.hpp)
+void BlockGIOracle::seqReset(int n)
+{
+  n_ = n;
+  seq_.clear();
+  qdata_.clear();
+}
+
+void BlockGIOracle::seqAddHouseholder(int start, int len, const double * essential, double tau)
+{
+  Rec h{0, start, len, qdata_.size()};
+  qdata_.resize(qdata_.size() + static_cast<size_t>(len));
+  double * p = qdata_.data() + h.off;
+  p[0] = tau;
+  for(int i = 1; i < len; ++i) p[i] = essential[i - 1];
+  seq_.push_back(h);
+}
+
+void BlockGIOracle::seqAddGivens(int start, int count, const double * c, const double * s)
+{
+  Rec h{1, start, count, qdata_.size()};
+  qdata_.resize(qdata_.size() + 2 * static_cast<size_t>(count));
+  double * p = qdata_.data() + h.off;
+  for(int i = 0; i < count; ++i)
+  {
+    p[i] = c[i];
+    p[count + i] = s[i];
+  }
+  seq_.push_back(h);
+}
+
+void BlockGIOracle::makeHouseholder(const double * x, int len, double * essential, double & tau, double & beta)
+{
+  const double c0 = x[0];
+  const double tailSq = len == 1 ? 0.0 : dot32(len - 1, x + 1, x + 1);
+  if(tailSq <= DBL_MIN)
+  {
+    tau = 0;
+    beta = c0;
+    for(int i = 1; i < len; ++i) essential[i - 1] = 0;
+  }
+  else
+  {
+    beta = std::sqrt(std::fma(c0, c0, tailSq));
+    if(c0 >= 0) beta = -beta;
+    const double den = c0 - beta;
+    for(int i = 1; i < len; ++i) essential[i - 1] = x[i] / den;
+    tau = (beta - c0) / beta;
+  }
+}
+
 } // namespace block_oracle
 
 // ---------------------------------------------------------------------------------------------
@@ -643,4 +695,32 @@ extern "C" int block_oracle_solve_batch(int type,
     for(auto & t : th) t.join();
   }
   return worst.load();
+}
+
+// ---- test hooks: OrthonormalSequence alone
+extern "C" void * block_oracle_seq_create(int n)
+{
+  auto * o = new block_oracle::BlockGIOracle();
+  o->seqReset(n);
+  return o;
+}
+extern "C" void block_oracle_seq_destroy(void * h)
+{
+  delete static_cast<block_oracle::BlockGIOracle *>(h);
+}
+extern "C" void block_oracle_seq_add_householder(void * h, int start, int len, const double * essential, double tau)
+{
+  static_cast<block_oracle::BlockGIOracle *>(h)->seqAddHouseholder(start, len, essential, tau);
+}
+extern "C" void block_oracle_seq_add_givens(void * h, int start, int count, const double * c, const double * s)
+{
+  static_cast<block_oracle::BlockGIOracle *>(h)->seqAddGivens(start, count, c, s);
+}
+extern "C" void block_oracle_seq_apply(void * h, double * v, int transpose)
+{
+  static_cast<block_oracle::BlockGIOracle *>(h)->seqApply(v, transpose != 0);
+}
+extern "C" void block_oracle_make_householder(const double * x, int len, double * essential, double * tau, double * beta)
+{
+  block_oracle::BlockGIOracle::makeHouseholder(x, len, essential, *tau, *beta);
 }

@@ -94,6 +94,13 @@ public:
   int nbVar() const { return n_; }
   int nbCstr() const { return mc_; }
   long qDoubles() const { return static_cast<long>(qdata_.size()); } // size of the stored sequence
+  // ---- test hooks: the OrthonormalSequence alone (tests/InternalTest.cpp:35-323 restated in tests/test_orthonormal_sequence.py)
+  void seqReset(int n);
+  void seqAddHouseholder(int start, int len, const double * essential, double tau); // H = I - tau e e^T, e = [1; essential(len-1)]
+  void seqAddGivens(int start, int count, const double * c, const double * s); // rotations (start+i, start+i+1), i = 0 .. count-1
+  void seqApply(double * v, bool transpose) const { transpose ? applyQt(v) : applyQ(v); }
+  // makeHouseholder as StructuredQR::add does it on d.tail(len) (src/structured/StructuredQR.cpp:75): returns tau, beta, essential
+  static void makeHouseholder(const double * x, int len, double * essential, double & tau, double & beta);
   int qRecords() const { return static_cast<int>(seq_.size()); }
 
 private:
