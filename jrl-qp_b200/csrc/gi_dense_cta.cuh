@@ -71,6 +71,13 @@ namespace jrlqp
                                 // while the current one is solved. Measured (profiles/r02u_ab_*.txt): -0.4 % at n = 50 and n = 128, -2.8 % at n = 20 — the
                                 // staging loads are not what these kernels wait for (long_scoreboard 4 % of the stall samples): off
 #endif
+#ifndef JRLQP_ZPART_W1
+#  define JRLQP_ZPART_W1 1 // (+1.3 % at n = 50, profiles/r03a_ab_A.txt) W == 2: in the main iterations (short Givens chain, long back substitution) the z-dependent half of the step length runs on warp 1
+#endif
+#ifndef JRLQP_SEEDS_IN_Z
+#  define JRLQP_SEEDS_IN_Z 1 // (+1.6 % at n = 50, neutral at n = 128, profiles/r03b_ab_*.txt) W > 1: the seeds of the Givens recurrence are computed by ALL the threads next to z = J2 d2 (one element each)
+                             // instead of by the chain warp in chunks of 32 before its recurrence
+#endif
 #ifndef JRLQP_MINB1
 #  define JRLQP_MINB1 16 // resident CTAs per SM the one-warp kernel is compiled for (register cap 65536 / (32 * MINB1))
 #endif
@@ -703,7 +710,13 @@ struct GiCta
 #endif
   // inner loops of the Cholesky and of J = L^-T: unrolled four times in the wide kernels (+3 % at n = 128; -0.5 % at n = 50 and
   // -9 % at n = 20, profiles/r01zn_ab_*.txt)
-  static constexpr int UNR_CHOL = W >= 3 ? JRLQP_UNR_CHOL : 1, UNR_JB = W >= 3 ? JRLQP_UNR_JB : 1;
+#ifndef JRLQP_UNR_CHOL_NARROW
+#  define JRLQP_UNR_CHOL_NARROW 1
+#endif
+#ifndef JRLQP_UNR_JB_NARROW
+#  define JRLQP_UNR_JB_NARROW 1
+#endif
+  static constexpr int UNR_CHOL = W >= 3 ? JRLQP_UNR_CHOL : JRLQP_UNR_CHOL_NARROW, UNR_JB = W >= 3 ? JRLQP_UNR_JB : JRLQP_UNR_JB_NARROW;
   static constexpr int UNR_DZ = W >= 3 ? 4 : JRLQP_UNR_DZ; // unroll factor of the d = J^T n+ and z = J2 d2 loops
   static constexpr int PF = W == 1 ? JRLQP_PF1 : (W == 2 ? JRLQP_PF2 : JRLQP_PF4); // rotations per chunk when the Givens table is applied
   // ---- immutable per-launch
@@ -1828,6 +1841,20 @@ struct GiCta
     sync();
     PH_MARK(3); // d
 
+    // (seeds of the Givens recurrence, part 1: suffix sums of d_j^2 inside the warp, warp totals to shared memory)
+    double sfx = 0.0, dj_seed = 0.0;
+    if(SEEDS_IN_Z)
+    {
+      dj_seed = (j >= q && j < n) ? ds[j] : 0.0;
+      sfx = dj_seed * dj_seed;
+#pragma unroll
+      for(int off = 1; off < 32; off <<= 1)
+      {
+        const double t = __shfl_down_sync(JRLQP_FULL, sfx, off);
+        if(lane + off < 32) sfx = sfx + t;
+      }
+      if(lane == 0) scr[2 + warp] = sfx;
+    }
     // z, thread = row: z[i] = dot4_{j=q..n-1}(J(i,j), d[j]), accumulator (j-q)&3
     {
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -1850,6 +1877,34 @@ struct GiCta
     // the two serial recurrences, concurrently on different warps when W > 1
     sync();
     PH_MARK(4); // z
+    if(SEEDS_IN_Z)
+    {
+      // part 2: S_j = d_j^2 + d_{j+1}^2 + ... ~ rho_j^2, then the seeds of link j - 1 (see givens_recurrence); the chain warp
+      // alone waits for them (named barrier 3: the other warps only arrive)
+      double S = sfx;
+      for(int w = warp + 1; w < W; ++w) S = S + scr[2 + w];
+      double rsd = rsqrt_seed(S);
+      if(j == n - 1) rsd = dj_seed < 0.0 ? -rsd : rsd;
+      const double t = ds[j - 1] * rsd; // (j == 0: an unused read of the padding before d)
+      const double ss = fma(t, t, 1.0);
+      const double ysd = rsqrt_seed(ss);
+      if(j >= q && j < n)
+      {
+        if(j > q)
+        {
+          grec[2 * (j - 1)] = make_double2(rsd, ss * ysd);
+          double2 hk = make_double2(0.5 * ysd, 0.0);
+          rec_kind(hk) = 3 | 8;
+          grec[2 * (j - 1) + 1] = hk;
+        }
+        else
+          scr[11] = rsd;
+      }
+      if(warp == (W > 1 ? 1 : 0))
+        asm volatile("bar.sync 3, %0;" ::"n"(32 * W) : "memory");
+      else
+        asm volatile("bar.arrive 3, %0;" ::"n"(32 * W) : "memory");
+    }
   }
 
   // r = R^-1 d(0:q): column-oriented back substitution with true division (r_k = w_k / R(k,k), then
@@ -1960,6 +2015,7 @@ struct GiCta
   // grec[2i+1] = (h_i, then the incoming rho ; branch taken | 8 if the link is to be proven), where the seeds are
   // rs ~ 1 / rho, g ~ u, h ~ 1 / (2 u). Every lane stores (same value, same address): no predicate in the loop.
   static constexpr bool SPLIT_CHAIN = JRLQP_OPT_CS && W > 1;
+  static constexpr bool SEEDS_IN_Z = JRLQP_SEEDS_IN_Z && W > 1;
   static constexpr int CHAIN_UNR = W >= 3 ? 2 : JRLQP_CHAIN_UNR;
   static constexpr bool CHAIN_VOTE = W >= 3 ? false : (JRLQP_CHAIN_VOTE != 0); // measured: profiles/r02j_ab_*.txt
   __device__ __forceinline__ static int & rec_kind(double2 & r) { return reinterpret_cast<int *>(&r.y)[0]; }
@@ -1967,6 +2023,8 @@ struct GiCta
   {
     double2 * const rec = grec;
     // ---- seeds: element j = top - lane of d, chunks of 32 from the last element down; suffix sums by a warp scan
+    //      (SEEDS_IN_Z: already computed by all the threads in compute_step)
+    if(!SEEDS_IN_Z)
     {
       double carry = 0.0;
 #pragma unroll 1
@@ -2569,23 +2627,27 @@ struct GiCta
         }
         PH_MARK(11);
         compute_step(sc);
-        const int zw = (SPEC && want_next) ? SW : 0; // the warp that evaluates the z-dependent half of the step length
+        // the warp that evaluates the z-dependent half of the step length
+        const int zw = SPEC ? (want_next ? SW : 0) : ((JRLQP_ZPART_W1 && W == 2 && !pre) ? 1 : 0);
         double t2 = 0.0, nz = 0.0;
         bool zpos = false;
         if(warp == zw)
         {
           len_z(sc, !pre && !skip, cx_sel, t2, nz, zpos);
           PH_MARK(7);
-          if(SPEC && zw != 0)
+          if(W > 1 && zw != 0)
           {
             const double ts = pre ? (zpos ? t2 : 0.0) : t2; // the length of a full step (pre-activation: the exact step)
-            const bool spec = ts < big;
-            __syncwarp(); // cv has been read by every lane
-#pragma unroll
-            for(int s = 0; s < W; ++s)
+            const bool spec = SPEC && ts < big;
+            if(SPEC)
             {
-              const int r = lane + 32 * s;
-              if(r < n) xs2[r] = fma(ts, zs[r], xs[r]);
+              __syncwarp(); // cv has been read by every lane
+#pragma unroll
+              for(int s = 0; s < W; ++s)
+              {
+                const int r = lane + 32 * s;
+                if(r < n) xs2[r] = fma(ts, zs[r], xs[r]);
+              }
             }
             if(lane == 0)
             {
@@ -2595,8 +2657,8 @@ struct GiCta
               dec[4] = spec;
             }
             asm volatile("bar.arrive 1, 64;" ::: "memory"); // hand t2, n+.z over to warp 0 (which waits with bar.sync 1)
-            if(NSW > 1) asm volatile("bar.sync 2, %0;" ::"n"(32 * (NSW > 1 ? NSW : 1)) : "memory"); // x + t2 z is visible to the other scan warps
-            scan_now = spec;
+            if(SPEC && NSW > 1) asm volatile("bar.sync 2, %0;" ::"n"(32 * (NSW > 1 ? NSW : 1)) : "memory"); // x + t2 z is visible to the other scan warps
+            if(SPEC) scan_now = spec;
           }
         }
         else if(SPEC && NSW > 1 && zw != 0 && warp > SW)
@@ -2617,7 +2679,7 @@ struct GiCta
           PH_MARK(5);
           double t1;
           len_t1(t1, l, !pre);
-          if(SPEC && zw != 0)
+          if(W > 1 && zw != 0)
           {
             asm volatile("bar.sync 1, 64;" ::: "memory");
             t2 = decd[1];
