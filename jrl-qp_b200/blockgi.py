@@ -147,9 +147,12 @@ class BatchedBlockGISolver:
         return TerminationStatus(rc)
 
     def solve_device(self, B, G, a, Cd, bl, bu, xl, xu, x, u=None, f=None, iterations=None, status=None, active_set=None,
-                     active_list=None, n_active=None, shared=(), stream=None):
-        """DEVICE pointers (ints, torch tensors); asynchronous on `stream`. `shared`: names of stride-0 arrays."""
+                     active_list=None, n_active=None, shared=(), stream=None, G_stride=None):
+        """DEVICE pointers (ints, torch tensors); asynchronous on `stream`. `shared`: names of stride-0 arrays.
+        G_stride: elements between the instances of G when they are not packed back to back."""
         pb = self._problem(B, G, a, Cd, bl, bu, xl, xu, set(shared))
+        if G_stride is not None:
+            pb.G_stride = int(G_stride)
         res = _Result(_ptr(x), _ptr(u), _ptr(f), _ptr(iterations), _ptr(status), _ptr(active_set), _ptr(active_list), _ptr(n_active), None)
         rc = self._lib.jrlqp_blockgi_solve_device(self._h, C.byref(pb), C.byref(res), C.c_void_p(stream or 0))
         if rc != 0:

@@ -5,6 +5,7 @@
 #include "structured_host.hpp"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -45,6 +46,9 @@ struct jrlqp_blockgi
   long long d_out_bytes = 0;
   cudaStream_t stream = nullptr;
   int bthreads = 0; // threads per CTA of blockgi_kernel (the structured kernels keep s->g->threads)
+  int flags = 7; // BGF_* fast paths (blockgi.cuh); JRLQP_BLOCKGI_FAST overrides
+  int fast_nb = 0; // uniform dense tile size of a tri-block-diagonal G (8 / 12 / 16), else 0
+  void (*kernel)(const BlockGiParams) = nullptr;
   std::string err;
 
   bool check(cudaError_t e, const char * what)
@@ -64,7 +68,11 @@ int configure(jrlqp_blockgi * s)
   cudaDeviceProp prop;
   SCK(cudaGetDeviceProperties(&prop, s->device));
   const int m = s->mc + s->nb;
-  const long long smem = BlockGi::smem_bytes(s->n, s->g->nmax, m, std::max(1, s->opt.max_iter));
+  s->fast_nb = s->g->small_nb;
+  s->flags = 7;
+  if(const char * e = getenv("JRLQP_BLOCKGI_FAST")) s->flags = atoi(e) & 7;
+  s->kernel = s->n <= 512 ? blockgi_kernel<4> : blockgi_kernel<8>; // entries of a reflector per thread: 128 classes x 4 / 8
+  const long long smem = BlockGi<8>::smem_bytes(s->n, s->g->nmax, m, std::max(1, s->opt.max_iter), s->fast_nb, s->g->b);
   if(smem > (long long)prop.sharedMemPerBlockOptin)
   {
     s->err = "problem does not fit in shared memory (n, block size or max_iter too large)";
@@ -73,11 +81,10 @@ int configure(jrlqp_blockgi * s)
   s->smem = (int)smem;
   if(s->bthreads == 0)
   {
-    s->bthreads = std::max(128, s->g->threads); // the Householder records are applied by the whole CTA over 128 classes (blockgi.cuh)
-    if(const char * e = getenv("JRLQP_BLOCKGI_THREADS")) s->bthreads = std::max(128, std::min(1024, atoi(e) / 32 * 32)); // (>= 128: one class of the reflector products per thread)
+    s->bthreads = 128; // one class of the reflector products per thread (blockgi.cuh); the kernel is compiled for 128 threads
   }
-  SCK(jrlqp::raise_smem_limit(blockgi_kernel, s->smem));
-  SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ, blockgi_kernel, s->bthreads, s->smem));
+  SCK(jrlqp::raise_smem_limit(s->kernel, s->smem));
+  SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ, s->kernel, s->bthreads, s->smem));
   if(s->occ < 1)
   {
     s->err = "kernel cannot be made resident";
@@ -298,8 +305,12 @@ int jrlqp_blockgi_solve_device(jrlqp_blockgi * s, const jrlqp_block_problem * pb
   p.qcap = s->qcap;
   p.batch = pb->batch;
   p.ticket = s->d_ticket;
+  // the warp-level solves stream the tiles by bulk copies: 16-byte aligned instances (the offsets inside one are even)
+  const bool aligned = (reinterpret_cast<uintptr_t>(gdata) % 16) == 0 && (p.G.stride % 2) == 0;
+  p.fast_nb = aligned ? s->fast_nb : 0;
+  p.flags = s->flags;
   const long long grid = std::min<long long>(pb->batch, s->grid);
-  blockgi_kernel<<<(unsigned)grid, s->bthreads, s->smem, stream>>>(p);
+  s->kernel<<<(unsigned)grid, s->bthreads, s->smem, stream>>>(p);
   count_launch();
   SCK(cudaGetLastError());
   return JRLQP_OK;
@@ -430,7 +441,9 @@ extern "C" int jrlqp_blockgi_test_sequence(int32_t device, int32_t n, int32_t nr
     p.ws = d_ws;
     p.ws_stride = 0;
     p.qcap = qlen;
-    const int smem = (int)BlockGi::smem_bytes(n, 1, 0, p.max_iter);
+    p.flags = 7;
+    if(const char * e = getenv("JRLQP_BLOCKGI_FAST")) p.flags = atoi(e) & 7;
+    const int smem = (int)BlockGi<8>::smem_bytes(n, 1, 0, p.max_iter, 0, 0);
     ok = jrlqp::raise_smem_limit(blockgi_sequence_test_kernel, smem) == cudaSuccess;
     if(ok)
     {

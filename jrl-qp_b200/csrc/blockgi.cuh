@@ -26,10 +26,19 @@
 // bit-identical to the CPU oracle.
 #pragma once
 
+#include "fp64_exact.cuh"
 #include "structured.cuh"
 
 namespace jrlqp
 {
+
+// fast paths of the kernel (BlockGiParams::flags; all on by default, JRLQP_BLOCKGI_FAST overrides for A/B runs and tests)
+enum : int
+{
+  BGF_WARP_SOLVE = 1, // structured solves on one warp, tiles streamed by TMA bulk copies (needs fast_nb != 0)
+  BGF_REG_SEQUENCE = 2, // orthonormal sequence applied to a vector held in registers, one barrier per reflector
+  BGF_BLOCKED_RSOLVE = 4 // R^-1 d1 blocked by 16 columns: register-resident triangle on one warp + panel update by the CTA
+};
 
 struct BlockGiParams
 {
@@ -55,6 +64,8 @@ struct BlockGiParams
   long long * qdoubles; // nullable: doubles of Q storage used (statistic)
   double * ws; // per-CTA workspace: R packed (n (n + 1) / 2), then the Q records (qcap)
   long long ws_stride, qcap;
+  int fast_nb; // tile size of a tri-block-diagonal chain of uniform dense tiles at 16-byte aligned offsets (8 / 12 / 16), else 0
+  int flags; // BGF_*
   long long batch;
   unsigned long long * ticket;
 };
@@ -107,13 +118,39 @@ __device__ __forceinline__ void bg_make_givens(double p, double q, double & c, d
   }
 }
 
+// 1 / d to a few ulps from the hardware seed (3 Newton steps): the reciprocal a proven quotient starts from
+// (fp64_exact.cuh div_rcp: the result never depends on it)
+__device__ __forceinline__ double bg_rcp(double d)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
+__device__ __forceinline__ unsigned bg_smem_addr(const void * p)
+{
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+// ME: entries of a reflector / of a vector per thread in the passes over Q (128 classes x ME >= n)
+template<int ME>
 struct BlockGi
 {
+  static constexpr int RING = 4, AHEAD = RING - 1; // stage of the warp-level structured solves: tiles of RING blocks
+  static constexpr int RB = 16; // columns per block of the blocked R solve
   const BlockGiParams & P;
   const int n, mc, m, T, tid, lane, warp, W;
   const bool up;
   // shared memory
-  double *x, *z, *d, *w, *u, *r, *scr, *hred, *Lt, *Bt;
+  double *x, *z, *d, *w, *u, *r, *scr, *hred, *rtri, *Lt, *Bt, *ring;
+  double2 * dgp; // [RING][16] (L_kk, ~ 1 / L_kk) of the staged diagonal tiles
+  unsigned long long * bars;
+  long long *sdoff, *sooff;
   int *rec, *alist, *iscr;
   signed char * st;
   // per problem
@@ -122,6 +159,10 @@ struct BlockGi
   int q, nrec;
   long long qoff;
   double f;
+  unsigned rph; // phase parities of the ring's mbarriers (bit = slot), tracked by every lane of warp 0
+
+  static __host__ __device__ int ring_ld(int nb) { return nb == 16 ? 18 : nb; } // (16: padded columns, 16-way bank conflicts otherwise)
+  static __host__ __device__ long long ring_doubles(int nb) { return nb ? (long long)RING * 2 * nb * ring_ld(nb) + RING * 32 : 0; } // tiles + pairs
 
   __device__ BlockGi(const BlockGiParams & p, double * sm)
   : P(p), n(p.G.n), mc(p.mc), m(p.mc + p.nb), T(blockDim.x), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5),
@@ -135,22 +176,50 @@ struct BlockGi
     u = w + ne;
     r = u + ne;
     scr = r + ne;
-    hred = scr + 80; // 128 class sums + the scaled dot of a Householder application
-    Lt = hred + 136;
+    hred = scr + 80; // 2 x 128 class sums of a Householder application (double-buffered) + the scaled dot
+    rtri = hred + 264; // blocked R solve: RB x (R_kk, ~ 1 / R_kk, R_{k-1,k}, -)
+    Lt = rtri + 4 * RB;
     Bt = Lt + p.G.nmax * p.G.nmax;
-    rec = reinterpret_cast<int *>(Bt + p.G.nmax * p.G.nmax);
+    ring = Bt + p.G.nmax * p.G.nmax + ((2 * p.G.nmax * p.G.nmax) & 1); // 16-byte aligned (bulk copies)
+    dgp = reinterpret_cast<double2 *>(ring + (p.fast_nb ? ring_doubles(p.fast_nb) - RING * 32 : 0));
+    bars = reinterpret_cast<unsigned long long *>(ring + ring_doubles(p.fast_nb));
+    sdoff = reinterpret_cast<long long *>(bars + (p.fast_nb ? RING : 0));
+    sooff = sdoff + (p.fast_nb ? p.G.b : 0);
+    rec = reinterpret_cast<int *>(sooff + (p.fast_nb ? p.G.b : 0));
     alist = rec + 3 * p.max_iter;
     iscr = alist + n;
     st = reinterpret_cast<signed char *>(iscr + 16);
     double * slot = p.ws + (long long)blockIdx.x * p.ws_stride;
     Rg = slot;
     Qg = slot + (long long)n * (n + 1) / 2;
+    rph = 0u;
   }
 
-  static __host__ __device__ long long smem_bytes(int n, int nmax, int m, int max_iter)
+  static __host__ __device__ long long smem_bytes(int n, int nmax, int m, int max_iter, int fast_nb, int b)
   {
     const long long ne = (n + 2) & ~1;
-    return (6 * ne + 80 + 136 + 2LL * nmax * nmax) * 8 + (3LL * max_iter + n + 16) * 4 + ((m + 15) & ~15);
+    const long long tiles = 2LL * nmax * nmax + ((2LL * nmax * nmax) & 1);
+    const long long fast = fast_nb ? ring_doubles(fast_nb) + RING + 2LL * b : 0;
+    return (6 * ne + 80 + 264 + 4 * RB + tiles + fast) * 8 + (3LL * max_iter + n + 16) * 4 + ((m + 15) & ~15);
+  }
+
+  // once per kernel: barriers of the ring, block offsets of G in shared memory (the solves read them on their critical path)
+  __device__ void setup()
+  {
+    if(P.fast_nb)
+    {
+      if(tid == 0)
+      {
+        for(int i = 0; i < RING; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bg_smem_addr(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      for(int i = tid; i < P.G.b; i += T)
+      {
+        sdoff[i] = P.G.doff[i];
+        sooff[i] = i + 1 < P.G.b ? P.G.ooff[i] : 0;
+      }
+    }
+    __syncthreads();
   }
 
   __device__ __forceinline__ int pidx(int i) const { return up ? sg_perm(P.G, i) : i; }
@@ -223,7 +292,7 @@ struct BlockGi
   // defines (oracle/block_oracle.hpp); every entry of the reflector is loaded once, all loads of a record in flight
   // together. Round 1 applied a record with one warp: 12 dependent L2 round trips per pass at n = 384, two passes per
   // record, ~100 records, twice per iteration — 95 % of a solve (profiles/r01zc_blockgi_E_tri.json: 4.8 k QP/s).
-  static constexpr int MAXE = 8; // entries of a reflector per thread: 128 classes x 8 >= n (n <= 1024)
+  static constexpr int MAXE = ME; // entries of a reflector per thread: 128 classes x ME >= n (n <= 512: 4, n <= 1024: 8)
 
   // entries k = tid, tid + 128, ... of the reflector of record e (1.0 for the implicit leading entry), and its tau:
   // loaded one record AHEAD of their use, so that the L2 / HBM latency of a record hides behind the reduction of the
@@ -272,10 +341,10 @@ struct BlockGi
     {
       double acc = (hred[lane] + hred[lane + 32]) + (hred[lane + 64] + hred[lane + 96]);
       for(int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(BG_FULL, acc, off);
-      if(lane == 0) hred[128] = tau * acc;
+      if(lane == 0) hred[256] = tau * acc;
     }
     __syncthreads();
-    const double hd = hred[128];
+    const double hd = hred[256];
     if(tid < 128)
     {
 #pragma unroll
@@ -288,8 +357,56 @@ struct BlockGi
     __syncthreads();
   }
 
+  // one Givens record (c[size], s[size] at p) applied by warp 0 to vs[0 .. size] in shared memory
+  __device__ __forceinline__ void givens_record(double * vs, const double * p, const int size, const int dir)
+  {
+    if(dir > 0)
+    {
+      // Givens(c, s)^T, i ascending: x' = c x - s y, y' = s x + c y; the y' of one rotation is the x of the next
+      double carry = vs[0];
+      for(int i0 = 0; i0 < size; i0 += 32)
+      {
+        const int k = min(i0 + lane, size - 1);
+        const double cl = p[k], sl = p[size + k];
+        const int cn = min(32, size - i0);
+#pragma unroll 4
+        for(int j = 0; j < cn; ++j)
+        {
+          const double c = __shfl_sync(BG_FULL, cl, j), sn = __shfl_sync(BG_FULL, sl, j);
+          const double xi = carry, yi = vs[i0 + j + 1];
+          const double nx = fma(c, xi, -(sn * yi));
+          carry = fma(c, yi, sn * xi);
+          if(lane == 0) vs[i0 + j] = nx;
+        }
+      }
+      if(lane == 0) vs[size] = carry;
+    }
+    else
+    {
+      // Givens(c, s), i descending: x' = c x + s y, y' = -s x + c y; the x' of one rotation is the y of the next
+      double carry = vs[size];
+      for(int i1 = size; i1 > 0; i1 -= 32)
+      {
+        const int cn = min(32, i1);
+        const int k = max(i1 - 1 - lane, 0);
+        const double cl = p[k], sl = p[size + k];
+#pragma unroll 4
+        for(int j = 0; j < cn; ++j)
+        {
+          const int i = i1 - 1 - j;
+          const double c = __shfl_sync(BG_FULL, cl, j), sn = __shfl_sync(BG_FULL, sl, j);
+          const double xi = vs[i], yi = carry;
+          carry = fma(c, xi, sn * yi);
+          const double ny = fma(c, yi, -(sn * xi));
+          if(lane == 0) vs[i + 1] = ny;
+        }
+      }
+      if(lane == 0) vs[0] = carry;
+    }
+  }
+
   // dir = +1: Q^T v (records in order of addition), dir = -1: Q v (reverse order)
-  __device__ void apply_sequence(double * v, const int dir)
+  __device__ void apply_sequence_smem(double * v, const int dir)
   {
     if(nrec > 0)
     {
@@ -306,51 +423,7 @@ struct BlockGi
           householder(pc, tc, size, vs);
         else
         {
-          const double * p = Qg + rec[3 * e + 2];
-          if(warp == 0)
-          {
-            if(dir > 0)
-            {
-              // Givens(c, s)^T, i ascending: x' = c x - s y, y' = s x + c y; the y' of one rotation is the x of the next
-              double carry = vs[0];
-              for(int i0 = 0; i0 < size; i0 += 32)
-              {
-                const int k = min(i0 + lane, size - 1);
-                const double cl = p[k], sl = p[size + k];
-                const int cn = min(32, size - i0);
-                for(int j = 0; j < cn; ++j)
-                {
-                  const double c = __shfl_sync(BG_FULL, cl, j), sn = __shfl_sync(BG_FULL, sl, j);
-                  const double xi = carry, yi = vs[i0 + j + 1];
-                  const double nx = fma(c, xi, -(sn * yi));
-                  carry = fma(c, yi, sn * xi);
-                  if(lane == 0) vs[i0 + j] = nx;
-                }
-              }
-              if(lane == 0) vs[size] = carry;
-            }
-            else
-            {
-              // Givens(c, s), i descending: x' = c x + s y, y' = -s x + c y; the x' of one rotation is the y of the next
-              double carry = vs[size];
-              for(int i1 = size; i1 > 0; i1 -= 32)
-              {
-                const int cn = min(32, i1);
-                const int k = max(i1 - 1 - lane, 0);
-                const double cl = p[k], sl = p[size + k];
-                for(int j = 0; j < cn; ++j)
-                {
-                  const int i = i1 - 1 - j;
-                  const double c = __shfl_sync(BG_FULL, cl, j), sn = __shfl_sync(BG_FULL, sl, j);
-                  const double xi = vs[i], yi = carry;
-                  carry = fma(c, xi, sn * yi);
-                  const double ny = fma(c, yi, -(sn * xi));
-                  if(lane == 0) vs[i + 1] = ny;
-                }
-              }
-              if(lane == 0) vs[0] = carry;
-            }
-          }
+          if(warp == 0) givens_record(vs, Qg + rec[3 * e + 2], size, dir);
           __syncthreads();
         }
 #pragma unroll
@@ -360,8 +433,475 @@ struct BlockGi
     }
     __syncthreads();
   }
+
+  // reflector of record e for this thread (entry k of v belongs to thread k mod 128): pk[j] = E[tid + 128 j - start] inside
+  // [start, end), 1.0 for the implicit leading entry, 0 elsewhere; st: start (sign bit: a Givens record), en: one past the end
+  __device__ __forceinline__ void fetch_record(const int e, const int kt, double (&pk)[MAXE], double & tau, int & st, int & en) const
+  {
+    const int s = rec[3 * e], sz = rec[3 * e + 1];
+    const double * p = Qg + rec[3 * e + 2];
+    st = s;
+    en = (s & 0x7fffffff) + sz;
+    tau = 0.0;
+    if(s >= 0) // (uniform)
+    {
+      tau = p[0];
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = kt + 128 * j;
+        const double t = (k >= s && k < en) ? p[k - s] : 0.0;
+        pk[j] = k == s ? 1.0 : t;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void prefetch_record_l2(const int e) const
+  {
+    const int len = rec[3 * e] >= 0 ? rec[3 * e + 1] : 2 * rec[3 * e + 1];
+    const double * p = Qg + rec[3 * e + 2];
+    if(8 * tid < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 8 * tid)); // one request per 64 bytes (128 threads: 1024 doubles >= n)
+    if(8 * tid + 1024 < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 8 * tid + 1024)); // (a Givens record of n > 512)
+  }
+
+  // one record applied to the register-resident vector (see apply_sequence_reg)
+  __device__ __forceinline__ void apply_record(const int e, const int dir, const int kt, double * v, double (&vr)[MAXE], const double (&pc)[MAXE],
+                                               const double tc, const int st, const int en, int & buf)
+  {
+    if(st >= 0)
+    {
+      double * h = hred + 128 * buf;
+      double acc = 0.0;
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = kt + 128 * j;
+        const double t = fma(pc[j], vr[j], acc);
+        acc = (k >= st && k < en) ? t : acc;
+      }
+      if(tid < 128) h[(tid - st) & 127] = acc;
+      __syncthreads();
+      double a4 = (h[lane] + h[lane + 32]) + (h[lane + 64] + h[lane + 96]);
+#pragma unroll
+      for(int off = 16; off >= 1; off >>= 1) a4 += __shfl_xor_sync(BG_FULL, a4, off);
+      const double hd = tc * a4;
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = kt + 128 * j;
+        const double t = fma(-hd, pc[j], vr[j]);
+        vr[j] = (k >= st && k < en) ? t : vr[j];
+      }
+      buf ^= 1;
+    }
+    else
+    {
+      // a Givens sequence is a serial chain over adjacent entries: through shared memory, on warp 0
+      const int s0 = st & 0x7fffffff; // rotations on the entries s0 .. en (en = s0 + number of rotations)
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = kt + 128 * j;
+        if(k >= s0 && k <= en) v[k] = vr[j];
+      }
+      __syncthreads();
+      if(warp == 0) givens_record(v + s0, Qg + rec[3 * e + 2], en - s0, dir);
+      __syncthreads();
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = kt + 128 * j;
+        if(k >= s0 && k <= en) vr[j] = v[k];
+      }
+    }
+  }
+
+  // ---- the same sequence with the vector in REGISTERS (round 2). Thread t (< 128) owns v[t], v[t + 128], ... for the
+  // whole pass, so a reflector needs ONE barrier (the 128 class sums through shared memory; every warp then folds and
+  // reduces them redundantly, no second barrier to hand the result back) instead of three, and nothing of v moves
+  // between records. The classes of the inner product are those of the oracle: entry k of a reflector that starts at
+  // `start` belongs to class k mod 128, i.e. to the thread that owns v[start + k] — thread t runs class (t - start) mod
+  // 128, ascending k in it: the same chains, folds and butterfly, the same bits. The next record is fetched into a second
+  // register set while the current one is applied (two sets used alternately: no copies), records further down the list
+  // are pulled into L2 (the list of a config-E solve, ~ 0.4 MB per CTA, does not stay there: profiles/r02y_*).
+  __device__ void apply_sequence_reg(double * v, const int dir)
+  {
+    constexpr int PFD = 6; // records of look-ahead of the L2 prefetch
+    if(nrec > 0)
+    {
+      const int kt = tid < 128 ? tid : 0x40000000; // (threads beyond the 128 classes own nothing)
+      double vr[MAXE];
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = kt + 128 * j;
+        vr[j] = k < n ? v[k] : 0.0;
+      }
+      double pa[MAXE], pb[MAXE], ta, tb = 0.0;
+      int sa, ea, sb = 0, eb = 0;
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j) pa[j] = pb[j] = 0.0;
+      int e = dir > 0 ? 0 : nrec - 1;
+      for(int a = 1; a < PFD && a < nrec; ++a) prefetch_record_l2(e + dir * a);
+      fetch_record(e, kt, pa, ta, sa, ea);
+      int buf = 0;
+      int left = nrec;
+#pragma unroll 1
+      for(;;)
+      {
+        if(left > PFD) prefetch_record_l2(e + dir * PFD);
+        if(left > 1) fetch_record(e + dir, kt, pb, tb, sb, eb);
+        apply_record(e, dir, kt, v, vr, pa, ta, sa, ea, buf);
+        e += dir;
+        if(--left == 0) break;
+        if(left > PFD) prefetch_record_l2(e + dir * PFD);
+        if(left > 1) fetch_record(e + dir, kt, pa, ta, sa, ea);
+        apply_record(e, dir, kt, v, vr, pb, tb, sb, eb, buf);
+        e += dir;
+        if(--left == 0) break;
+      }
+#pragma unroll
+      for(int j = 0; j < MAXE; ++j)
+      {
+        const int k = kt + 128 * j;
+        if(k < n) v[k] = vr[j];
+      }
+    }
+    __syncthreads();
+  }
+
+  __device__ void apply_sequence(double * v, const int dir)
+  {
+    if(P.flags & BGF_REG_SEQUENCE)
+      apply_sequence_reg(v, dir);
+    else
+      apply_sequence_smem(v, dir);
+  }
   __device__ void apply_qt(double * v) { apply_sequence(v, +1); }
   __device__ void apply_q(double * v) { apply_sequence(v, -1); }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Structured solves on ONE WARP for tri-block-diagonal chains of uniform dense tiles (P.fast_nb = 8 / 12 / 16; the MPC
+  // shape of BASELINE.json config 5). Round 1 ran sg_solve_inplace on the whole CTA: a tile load from L2 / HBM and two
+  // block barriers per column, with one true division every thread repeats — half of a solve (profiles/r02y_*). Here
+  //   * lane r owns row r of the block; the substitution is the uniform-pivot recurrence of the dense kernel: every lane
+  //     applies link k's update to the NEXT pivot itself (same fma, same operands as the lane that owns it), so a link is
+  //     one quotient + one fma on the dependent chain and every x_k ends up uniform in registers — the product with the
+  //     sub-diagonal tile of the next block needs no exchange at all;
+  //   * the quotient w_k / L_kk comes from a reciprocal prepared one block ahead and is PROVEN correctly rounded
+  //     (fp64_exact.cuh); a block with an unproven quotient is redone with true divisions;
+  //   * the tiles of the next RING - 1 blocks are in flight as TMA bulk copies (cp.async.bulk, completion on an mbarrier per
+  //     stage) while a block is solved; the other warps of the CTA wait at the closing barrier.
+  // Per-output operation order = structured.cuh / oracle/decomp_oracle.cpp (dot4 for the tile products, column-oriented
+  // substitution), hence the same bits. v: the vector in shared memory; hints as sg_solve_inplace.
+  // ------------------------------------------------------------------------------------------------------------
+  template<int NB>
+  __device__ __forceinline__ void ring_issue(const int i, const int is, const int slot)
+  {
+    // tiles of diagonal block i and (is >= 0) sub-diagonal block is into stage `slot`; lane 0 only
+    constexpr int LDT = NB == 16 ? 18 : NB, TT = NB * LDT;
+    double * Ls = ring + slot * 2 * TT;
+    const unsigned bar = bg_smem_addr(bars + slot);
+    const unsigned bytes = (is >= 0 ? 2u : 1u) * NB * NB * 8u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of this stage are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    for(int t = 0; t < (is >= 0 ? 2 : 1); ++t)
+    {
+      const double * src = base + (t == 0 ? sdoff[i] : sooff[is]);
+      double * dst = Ls + t * TT;
+      if(LDT == NB)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bg_smem_addr(dst)), "l"(src),
+                     "r"(NB * NB * 8u), "r"(bar)
+                     : "memory");
+      else
+        for(int c = 0; c < NB; ++c)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bg_smem_addr(dst + c * LDT)),
+                       "l"(src + c * NB), "r"(NB * 8u), "r"(bar)
+                       : "memory");
+    }
+  }
+
+  __device__ __forceinline__ void ring_wait(const int slot)
+  {
+    unsigned done = 0;
+    const unsigned bar = bg_smem_addr(bars + slot), par = (rph >> slot) & 1u;
+    while(!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(par) : "memory");
+    rph ^= 1u << slot;
+  }
+
+  // links [klo, khi) of the substitution with true divisions, one shuffle per link (partial first blocks, and the rare
+  // block whose fast quotients could not be proven)
+  template<int NB, bool TR>
+  __device__ __noinline__ double block_solve_exact(const double * Ls, double wr, const int klo, const int khi)
+  {
+    constexpr int LDT = NB == 16 ? 18 : NB;
+    const int lc = min(lane, NB - 1);
+#pragma unroll 1
+    for(int s = 0; s < khi - klo; ++s)
+    {
+      const int k = TR ? khi - 1 - s : klo + s;
+      const double xk = __shfl_sync(BG_FULL, wr, k) / Ls[k + k * LDT];
+      const double lr = TR ? Ls[k + lc * LDT] : Ls[lc + k * LDT];
+      const double nw = fma(-xk, lr, wr);
+      const bool upd = TR ? lane < k : (lane > k && lane < NB);
+      wr = lane == k ? xk : (upd ? nw : wr);
+    }
+    return wr;
+  }
+
+  // the whole block, uniform-pivot recurrence: per link one pair load (L_kk and its reciprocal, prepared a block ahead),
+  // three FMAs for the quotient, one for the next pivot, one for the lane's own row; straight-line code (selects, no
+  // branch). The quotients are PROVEN afterwards, link k by lane k (its pivot, its diagonal entry, its x_k); false: some
+  // proof failed, wr and xs are to be discarded.
+  template<int NB, bool TR>
+  __device__ __forceinline__ bool block_solve_fast(const double * Ls, const double2 * dp, double & wr, const double dg, double (&xs)[NB])
+  {
+    constexpr int LDT = NB == 16 ? 18 : NB;
+    const int lc = min(lane, NB - 1);
+    double wsave = 0.0;
+    double wp = __shfl_sync(BG_FULL, wr, TR ? NB - 1 : 0);
+#pragma unroll
+    for(int s = 0; s < NB; ++s)
+    {
+      const int k = TR ? NB - 1 - s : s;
+      const int kn = TR ? k - 1 : k + 1; // the next pivot
+      const double tn = s + 1 < NB ? __shfl_sync(BG_FULL, wr, kn) : 0.0; // w_kn before this link's update
+      const double2 dr = dp[k];
+      const double q0 = wp * dr.y;
+      const double e = fma(-dr.x, q0, wp);
+      const double xk = fma(e, dr.y, q0);
+      wsave = lane == k ? wp : wsave;
+      xs[k] = xk;
+      if(s + 1 < NB) wp = fma(-xk, TR ? Ls[k + kn * LDT] : Ls[kn + k * LDT], tn);
+      const double lr = TR ? Ls[k + lc * LDT] : Ls[lc + k * LDT];
+      const double nw = fma(-xk, lr, wr);
+      const bool upd = TR ? lane < k : lane > k;
+      wr = lane == k ? xk : (upd ? nw : wr);
+    }
+    const bool ok = lane >= NB || div_proof(wsave, dg, wr);
+    return __all_sync(BG_FULL, ok);
+  }
+
+  template<int NB, bool TR>
+  __device__ void tri_solve_warp(double * v, const int start, int end)
+  {
+    constexpr int LDT = NB == 16 ? 18 : NB, TT = NB * LDT;
+    static_assert(NB % 4 == 0 && NB <= 16, "tile size");
+    const int b = P.G.b;
+    const int lc = min(lane, NB - 1);
+    if(end < 0) end = n;
+    // blocks in processing order: forward i0, i0 + 1, ... (the first block the hint start touches, then all that follow);
+    // transposed i1, i1 - 1, ..., 0 (the first block below the hint end)
+    int first, cnt;
+    if(!TR)
+    {
+      first = max(0, (start + NB - 1) / NB - 1);
+      cnt = b - first;
+    }
+    else
+    {
+      if(end <= 0) return;
+      first = min(b - 1, (end - 1) / NB);
+      cnt = first + 1;
+    }
+    auto blk = [&](int j) { return TR ? first - j : first + j; };
+    auto issue = [&](int j)
+    {
+      if(lane == 0)
+      {
+        const int i = blk(j);
+        ring_issue<NB>(i, j == 0 ? -1 : (TR ? i : i - 1), j % RING);
+      }
+    };
+    // (L_kk, ~ 1 / L_kk) of the tile in stage `slot`, lane k the pair k; returns the lane's own L_kk
+    auto prepare = [&](int slot) -> double
+    {
+      const double dgv = (ring + slot * 2 * TT)[lc + lc * LDT];
+      if(lane < NB) dgp[slot * 16 + lane] = make_double2(dgv, bg_rcp(dgv));
+      return dgv;
+    };
+    __syncwarp();
+    for(int j = 0; j < AHEAD && j < cnt; ++j) issue(j);
+    ring_wait(0);
+    double dg = prepare(0);
+    double xs[NB];
+#pragma unroll
+    for(int k = 0; k < NB; ++k) xs[k] = 0.0;
+#pragma unroll 1
+    for(int j = 0; j < cnt; ++j)
+    {
+      const int i = blk(j);
+      const int slot = j % RING;
+      const double * Ls = ring + slot * 2 * TT;
+      const double * Ss = Ls + TT;
+      __syncwarp(); // every lane is done with the stage of block j - 1, which the next copy overwrites; pairs of block j visible
+      if(j + AHEAD < cnt) issue(j + AHEAD);
+      double dgn = 1.0;
+      if(j + 1 < cnt)
+      {
+        ring_wait((j + 1) % RING);
+        dgn = prepare((j + 1) % RING);
+      }
+      double wr = v[i * NB + lc];
+      if(j > 0)
+      {
+        // forward: w -= S_{i-1} x_{i-1} (S(r, k) at Ss[r + k LDT]); transposed: w -= S_i^T x_{i+1} (S(k, r) at Ss[k + r LDT])
+        double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+        for(int k = 0; k < NB; k += 4)
+        {
+          c0 = fma(TR ? Ss[k + lc * LDT] : Ss[lc + k * LDT], xs[k], c0);
+          c1 = fma(TR ? Ss[k + 1 + lc * LDT] : Ss[lc + (k + 1) * LDT], xs[k + 1], c1);
+          c2 = fma(TR ? Ss[k + 2 + lc * LDT] : Ss[lc + (k + 2) * LDT], xs[k + 2], c2);
+          c3 = fma(TR ? Ss[k + 3 + lc * LDT] : Ss[lc + (k + 3) * LDT], xs[k + 3], c3);
+        }
+        wr = wr - ((c0 + c1) + (c2 + c3));
+      }
+      // hints: only the first block can be partial (forward: rows from `start` on; transposed: rows before `end`)
+      int klo = 0, khi = NB;
+      if(j == 0)
+      {
+        if(!TR)
+          klo = max(0, start - i * NB);
+        else
+          khi = min(NB, end - i * NB);
+      }
+      const double w0 = wr;
+      bool fast = klo == 0 && khi == NB;
+      if(fast) fast = block_solve_fast<NB, TR>(Ls, dgp + slot * 16, wr, dg, xs);
+      if(!fast)
+      {
+        wr = block_solve_exact<NB, TR>(Ls, w0, klo, khi);
+#pragma unroll
+        for(int k = 0; k < NB; ++k) xs[k] = __shfl_sync(BG_FULL, wr, k);
+      }
+      if(lane < NB) v[i * NB + lane] = wr;
+      dg = dgn;
+    }
+  }
+
+  // StructuredG::solveL / solveInPlaceLTranspose on v (shared memory), every thread of the CTA; ends on a barrier
+  __device__ void g_solve(double * v, const bool transpose, const int start, const int end)
+  {
+    if(P.fast_nb && (P.flags & BGF_WARP_SOLVE))
+    {
+      if(warp == 0)
+      {
+        if(P.fast_nb == 8)
+        {
+          if(transpose)
+            tri_solve_warp<8, true>(v, start, end);
+          else
+            tri_solve_warp<8, false>(v, start, end);
+        }
+        else if(P.fast_nb == 12)
+        {
+          if(transpose)
+            tri_solve_warp<12, true>(v, start, end);
+          else
+            tri_solve_warp<12, false>(v, start, end);
+        }
+        else
+        {
+          if(transpose)
+            tri_solve_warp<16, true>(v, start, end);
+          else
+            tri_solve_warp<16, false>(v, start, end);
+        }
+      }
+      __syncthreads();
+    }
+    else
+      sg_solve_inplace(P.G, base, v, Lt, Bt, transpose, start, end);
+  }
+
+  // ---- r = R^-1 d1 (StructuredQR::RSolve), blocked by RB columns: the triangle of a block sits in the registers of warp 0
+  // (lane j: row k0 + j; every load of the block in flight at once, ONE L2 round trip per RB links instead of one per
+  // link), the substitution inside it is the uniform-pivot recurrence with proven quotients, and the rows above the block
+  // take the block's RB updates from all the threads (descending k for every entry: the order of the column-oriented
+  // loop, same bits). On entry w(0:q) = d(0:q), visible to every thread.
+  __device__ void r_solve_blocked()
+  {
+    for(int k1 = q; k1 > 0; k1 -= RB)
+    {
+      const int k0 = max(0, k1 - RB), nbk = k1 - k0;
+      if(warp == 0)
+      {
+        const int lc = min(lane, nbk - 1);
+        const double w0 = w[k0 + lc];
+        bool done;
+        {
+          // column k0 + c of the triangle in Tc[c] (row k0 + lane; rows below the diagonal read the diagonal). A partial
+          // block (the last one: nbk < RB) runs the same straight-line code with its missing links switched off.
+          double Tc[RB];
+#pragma unroll
+          for(int c = 0; c < RB; ++c)
+          {
+            const int cc = min(c, nbk - 1);
+            Tc[c] = Rg[colR(k0 + cc) + k0 + min(lc, cc)];
+          }
+          // link c reads (R_cc, ~ 1 / R_cc, R_{c-1,c}): written by lane c from two loads of its own (no register indexed by the lane)
+          const double dg = Rg[colR(k0 + lc) + k0 + lc];
+          const double sup = Rg[colR(k0 + lc) + k0 + max(lc - 1, 0)];
+          if(lane < RB) reinterpret_cast<double4 *>(rtri)[lane] = make_double4(dg, bg_rcp(dg), sup, 0.0);
+          const double4 * tri = reinterpret_cast<const double4 *>(rtri);
+          __syncwarp();
+          double wj = w0, rv = 0.0, wsave = 0.0;
+          double wp = __shfl_sync(BG_FULL, wj, nbk - 1);
+#pragma unroll
+          for(int c = RB - 1; c >= 0; --c)
+          {
+            const bool act = c < nbk; // (uniform)
+            const double tn = __shfl_sync(BG_FULL, wj, c > 0 ? c - 1 : 0);
+            const double4 t4 = tri[c];
+            const double q0 = wp * t4.y;
+            const double e = fma(-t4.x, q0, wp);
+            const double rk = fma(e, t4.y, q0);
+            wsave = (act && lane == c) ? wp : wsave;
+            rv = (act && lane == c) ? rk : rv;
+            if(c > 0)
+            {
+              const double wn = fma(-rk, t4.z, tn);
+              wp = act ? wn : wp;
+            }
+            const double nw = fma(-rk, Tc[c], wj);
+            wj = (act && lane < c) ? nw : wj;
+          }
+          const bool ok = lane >= nbk || div_proof(wsave, dg, rv);
+          done = __all_sync(BG_FULL, ok);
+          if(done && lane < nbk) r[k0 + lane] = rv;
+          __syncwarp();
+        }
+        if(!done)
+        {
+          // an unproven quotient (rare): one link at a time, true divisions
+          double wj = w0, rv = 0.0;
+          const double dg = Rg[colR(k0 + lc) + k0 + lc];
+#pragma unroll 1
+          for(int c = nbk - 1; c >= 0; --c)
+          {
+            const double rk = __shfl_sync(BG_FULL, wj, c) / __shfl_sync(BG_FULL, dg, c);
+            const double tc = Rg[colR(k0 + c) + k0 + min(lc, c)];
+            rv = lane == c ? rk : rv;
+            const double nw = fma(-rk, tc, wj);
+            wj = lane < c ? nw : wj;
+          }
+          if(lane < nbk) r[k0 + lane] = rv;
+        }
+      }
+      __syncthreads();
+      for(int j = tid; j < k0; j += T)
+      {
+        double wv = w[j];
+#pragma unroll
+        for(int c = RB - 1; c >= 0; --c)
+          if(c < nbk) wv = fma(-r[k0 + c], Rg[colR(k0 + c) + j], wv);
+        w[j] = wv;
+      }
+      __syncthreads();
+    }
+  }
 
   // ---- selectViolatedConstraint_ (src/experimental/BlockGISolver.cpp:111-164)
   __device__ __forceinline__ void slacks(int i, double & sl, double & su) const
@@ -466,7 +1006,7 @@ struct BlockGi
       he = b + 1;
     }
     __syncthreads();
-    sg_solve_inplace(P.G, base, w, Lt, Bt, false, hs, he);
+    g_solve(w, false, hs, he);
     const bool neg = status == BG_UPPER;
     for(int i = tid; i < n; i += T) d[i] = neg ? -w[i] : w[i];
     __syncthreads();
@@ -475,12 +1015,17 @@ struct BlockGi
     for(int i = tid; i < n; i += T) w[i] = i < q ? 0.0 : d[i];
     __syncthreads();
     apply_q(w);
-    sg_solve_inplace(P.G, base, w, Lt, Bt, true, 0, -1);
+    g_solve(w, true, 0, -1);
     for(int i = tid; i < n; i += T) z[i] = w[pidx(i)];
     __syncthreads();
     // r = R^-1 d1 (StructuredQR::RSolve): column-oriented back substitution, true division
     for(int k = tid; k < q; k += T) w[k] = d[k];
     __syncthreads();
+    if(P.flags & BGF_BLOCKED_RSOLVE)
+    {
+      r_solve_blocked();
+      return;
+    }
     for(int k = q - 1; k >= 0; --k)
     {
       const double * Rk = Rg + colR(k);
@@ -689,8 +1234,8 @@ struct BlockGi
     // initializePrimalDualPoints (:476-481): x = -G^-1 a, f = 0.5 a.x
     for(int i = tid; i < n; i += T) w[pidx(i)] = a[i];
     __syncthreads();
-    sg_solve_inplace(P.G, base, w, Lt, Bt, false, 0, -1);
-    sg_solve_inplace(P.G, base, w, Lt, Bt, true, 0, -1);
+    g_solve(w, false, 0, -1);
+    g_solve(w, true, 0, -1);
     for(int i = tid; i < n; i += T) x[i] = -w[pidx(i)];
     f = 0.5 * block_dot32(n, a, x);
 
@@ -807,11 +1352,16 @@ struct BlockGi
   }
 };
 
-__global__ void blockgi_kernel(const BlockGiParams P)
+#ifndef JRLQP_BG_MINB
+#  define JRLQP_BG_MINB 4 // resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 MINB); measured: profiles/r4d_*)
+#endif
+template<int ME>
+__global__ void __launch_bounds__(128, JRLQP_BG_MINB) blockgi_kernel(const BlockGiParams P)
 {
   extern __shared__ __align__(16) double sm[];
   __shared__ long long next;
-  BlockGi S(P, sm);
+  BlockGi<ME> S(P, sm);
+  S.setup();
   for(;;)
   {
     __syncthreads();
@@ -829,7 +1379,7 @@ __global__ void blockgi_kernel(const BlockGiParams P)
 __global__ void blockgi_sequence_test_kernel(const BlockGiParams P, const int * rec_in, int nrec, double * v, int ncases, int transpose)
 {
   extern __shared__ __align__(16) double sm[];
-  BlockGi S(P, sm);
+  BlockGi<8> S(P, sm);
   for(int i = threadIdx.x; i < 3 * nrec; i += blockDim.x) S.rec[i] = rec_in[i];
   S.nrec = nrec;
   for(int cs = blockIdx.x; cs < ncases; cs += gridDim.x)

@@ -328,6 +328,34 @@ static int configure_kernel(jrlqp_solver * s)
     s->lay = layN;
   }
   s->stage = stage;
+  if(s->warps == 3 && s->occ > 0)
+  {
+    // register-capped instantiation of the three-warp kernel: taken when it makes more QPs resident (with C staged only
+    // if that costs no residency, as above)
+    auto occ_of = [&](KernelFn fc, int smem) -> int
+    {
+      int o = 0;
+      if(smem <= 0 || smem > s->max_smem_optin) return 0;
+      if(jrlqp::raise_smem_limit(fc, smem) != cudaSuccess || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fc, 96, smem) != cudaSuccess)
+      {
+        cudaGetLastError();
+        return 0;
+      }
+      return o;
+    };
+    const int ocN = occ_of(gi_dense_cta_kernel<3, false, false, 4>, smN);
+    const int ocS = (s->stage_mode != 0 && occS > 0) ? occ_of(gi_dense_cta_kernel<3, true, false, 4>, smS) : 0;
+    const bool cstage = s->stage_mode == 1 ? ocS > 0 : (ocS > 0 && ocS >= ocN);
+    const int occC = cstage ? ocS : ocN;
+    if(occC > s->occ)
+    {
+      s->occ = occC;
+      s->stage = cstage;
+      s->smem_bytes = cstage ? smS : smN;
+      s->lay = cstage ? layS : layN;
+      s->kernel = cstage ? (KernelFn)gi_dense_cta_kernel<3, true, false, 4> : (KernelFn)gi_dense_cta_kernel<3, false, false, 4>;
+    }
+  }
   if(s->occ <= 0)
   {
     s->err = "problem does not fit in shared memory (n too large for the dense warp kernel)";

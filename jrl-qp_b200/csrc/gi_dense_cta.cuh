@@ -78,6 +78,9 @@ namespace jrlqp
 #  define JRLQP_SEEDS_IN_Z 1 // (+1.6 % at n = 50, neutral at n = 128, profiles/r03b_ab_*.txt) W > 1: the seeds of the Givens recurrence are computed by ALL the threads next to z = J2 d2 (one element each)
                              // instead of by the chain warp in chunks of 32 before its recurrence
 #endif
+#ifndef JRLQP_MINB3
+#  define JRLQP_MINB3 1 // resident CTAs per SM the three-warp kernel is compiled for (4: 168 registers, 12 warps per SM)
+#endif
 #ifndef JRLQP_MINB1
 #  define JRLQP_MINB1 16 // resident CTAs per SM the one-warp kernel is compiled for (register cap 65536 / (32 * MINB1))
 #endif
@@ -2928,8 +2931,12 @@ struct GiCta
 
 // Persistent kernel: grid = resident CTAs of the whole GPU; every CTA pulls the next problem index
 // from an atomic ticket counter, which absorbs the divergent iteration counts across QPs.
-template<int W, bool STAGE_C, bool WARM = false>
-__global__ void __launch_bounds__(32 * W, (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W == 2 ? 6 : 1)))) gi_dense_cta_kernel(const GiParams p)
+// MINB > 0: a second instantiation compiled for that many resident CTAs per SM (register cap). W = 3 only: 218 registers
+// leave 2 warps per scheduler, i.e. 2 CTAs per SM whatever the shared memory allows; capped at 168 registers the kernel
+// runs 3 QPs per SM where shared memory permits (n <= 77) and is 29 % faster there, 1.5 % slower where it does not
+// (profiles/r4a_ab_w3cap.txt) — the host picks by occupancy (capi.cu).
+template<int W, bool STAGE_C, bool WARM = false, int MINB = 0>
+__global__ void __launch_bounds__(32 * W, (MINB ? MINB : (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W == 2 ? 6 : (W == 3 ? JRLQP_MINB3 : 1)))))) gi_dense_cta_kernel(const GiParams p)
 {
   extern __shared__ __align__(16) double smem[];
   GiCta<W, STAGE_C, WARM> cta(p, smem);

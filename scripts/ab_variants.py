@@ -22,9 +22,15 @@ def main():
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--scan", type=int, default=-1)
+    ap.add_argument("--n", type=int, default=0, help="instead of --config: the test3 family of scripts/shape_sweep.py at this n")
     ap.add_argument("names", nargs="+")
     args = ap.parse_args()
-    ch = {"A": P.config_A, "B": P.config_B, "D": P.config_D}[args.config]()
+    if args.n > 0:
+        n_, ne = args.n, args.n * 20 // 100
+        ch = P.ProblemCharacteristics(n_, ne, n_, min(n_ - ne, n_) * 30 // 100, 0, n_ * 10 // 100, 0, True, True)
+        args.config = f"n{n_}"
+    else:
+        ch = {"A": P.config_A, "B": P.config_B, "D": P.config_D}[args.config]()
     pb = P.random_problems(ch, args.batch, seed=P.DEFAULT_SEED)
     dev = torch.device("cuda", 0)
     d = {k: torch.from_numpy(getattr(pb, k)).to(dev) for k in ("G", "a", "C", "bl", "bu", "xl", "xu")}
@@ -66,7 +72,7 @@ def main():
         t = np.array(times[name])
         same = bool(torch.equal(outs[name][0], ref[0]) and torch.equal(outs[name][1], ref[1]))
         print(f"{args.config} {name:8s} {Bn / t.min():12.0f} QP/s best  {Bn / np.median(t):12.0f} median  rounds {np.round(Bn / t / 1e3).astype(int).tolist()} k  "
-              f"identical_to_{args.names[0]}={same} regs={solvers[name].kernel_info()['regs_per_thread']}")
+              f"identical_to_{args.names[0]}={same} regs={solvers[name].kernel_info()['regs_per_thread']} qps_per_sm={solvers[name].kernel_info()['qps_per_sm']}")
 
 
 if __name__ == "__main__":

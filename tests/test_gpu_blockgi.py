@@ -77,6 +77,52 @@ def test_bit_exact_vs_oracle(type, sizes, mi, batch, bounds):
         assert bc.is_approx(g["x"][k], pb.x_planted[k], 1e-6)
 
 
+@pytest.mark.parametrize("fast", [0, 1, 2, 4, 7])
+@pytest.mark.parametrize("sizes,mi,batch,bounds", [
+    ([12] * 32, [12] * 32, 24, False),  # config E: aligned hints, full blocks only
+    ([12] * 6, [7] * 6, 32, True),      # bounds: hints in the middle of a tile (partial first block, exact links)
+    ([8] * 9, [5] * 9, 32, True),
+    ([16] * 5, [9] * 5, 32, True),      # padded stage columns
+])
+def test_fast_paths_bit_exact(sizes, mi, batch, bounds, fast, monkeypatch):
+    """Round 2 fast paths of the kernel (blockgi.cuh BGF_*): warp-level structured solves fed by TMA bulk copies, the
+    orthonormal sequence on a register-resident vector, the blocked R solve - each alone and all together, against the
+    oracle bit for bit (JRLQP_BLOCKGI_FAST is read when the solver is created)."""
+    monkeypatch.setenv("JRLQP_BLOCKGI_FAST", str(fast))
+    pb = bc.random_block_problem(Type.TriBlockDiagonal, sizes, mi, batch, seed=211 + len(sizes), bounds=bounds, shift=0.05)
+    sv, g, ref = _both(pb)
+    _assert_bit_exact(g, ref)
+    assert (g["status"] == 0).all() and g["iterations"].max() > 0
+
+
+def test_fast_paths_more_than_512_variables():
+    # 128 classes x 8 entries per thread in the passes over Q (n > 512), uniform tiles
+    pb = bc.random_block_problem(Type.TriBlockDiagonal, [12] * 44, [4] * 44, 4, seed=5, shift=0.05)
+    sv, g, ref = _both(pb)
+    _assert_bit_exact(g, ref)
+    assert (g["status"] == 0).all()
+
+
+def test_fast_paths_unaligned_instances_fall_back():
+    # an odd stride between instances: no bulk copies, the general solves run (same bits)
+    torch = pytest.importorskip("torch")
+    pb = bc.random_block_problem(Type.TriBlockDiagonal, [12] * 5, [6] * 5, 8, seed=17, shift=0.05)
+    B, n = 8, pb.n
+    dev = torch.device("cuda:0")
+    stride = pb.Gdata.shape[1] + 1
+    Gp = np.zeros((B, stride))
+    Gp[:, :-1] = pb.Gdata
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    G, a, Cd, bl, bu = t(Gp), t(pb.a), t(pb.Cdata), t(pb.bl), t(pb.bu)
+    x = torch.empty((B, n), dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    sv = BatchedBlockGISolver(pb.stG, pb.stC, False, B)
+    sv.solve_device(B, G, a, Cd, bl, bu, None, None, x, status=status, G_stride=stride)
+    torch.cuda.synchronize()
+    ref = po.block_solve_batch(pb.stG, pb.stC, pb.Gdata, pb.a, pb.Cdata, pb.bl, pb.bu)
+    assert np.array_equal(x.cpu().numpy(), ref["x"]) and (status.cpu().numpy() == 0).all()
+
+
 def test_unshifted_ill_conditioned():
     pb = bc.random_block_problem(Type.TriBlockDiagonal, [3, 5, 2, 3], [3, 3, 3, 3], 128, seed=77)
     sv, g, ref = _both(pb)

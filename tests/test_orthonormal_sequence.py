@@ -189,9 +189,11 @@ def test_make_householder_annihilates_the_tail():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fast", [7, 0])  # vector in registers, one barrier per reflector (round 2) / the shared-memory pass
 @pytest.mark.parametrize("threads", [128, 256])
 @pytest.mark.parametrize("name", list(_sequences()))
-def test_device_sequence_equals_oracle_and_dense_q(name, threads):
+def test_device_sequence_equals_oracle_and_dense_q(name, threads, fast, monkeypatch):
+    monkeypatch.setenv("JRLQP_BLOCKGI_FAST", str(fast))
     import jrl_qp_b200  # noqa: F401
     from jrl_qp_b200 import solver as S
     lib = S.load_library()
