@@ -141,13 +141,15 @@ __device__ __forceinline__ unsigned bg_smem_addr(const void * p)
 template<int ME>
 struct BlockGi
 {
-  static constexpr int RING = 4, AHEAD = RING - 1; // stage of the warp-level structured solves: tiles of RING blocks
+  static constexpr int RING = 3, AHEAD = RING - 1; // stage of the warp-level structured solves: tiles of RING blocks
+  static constexpr int QD = 3; // stage of the passes over Q: reflectors of QD records in flight (cp.async, thread-private slots)
   static constexpr int RB = 16; // columns per block of the blocked R solve
   const BlockGiParams & P;
   const int n, mc, m, T, tid, lane, warp, W;
   const bool up;
   // shared memory
-  double *x, *z, *d, *w, *u, *r, *scr, *hred, *rtri, *Lt, *Bt, *ring;
+  double *x, *z, *d, *w, *u, *r, *scr, *hred, *rtri, *qring, *rtau, *Lt, *Bt, *ring;
+  int MJ; // entries of a vector per thread in the passes over Q: ceil(n / 128) <= ME
   double2 * dgp; // [RING][16] (L_kk, ~ 1 / L_kk) of the staged diagonal tiles
   unsigned long long * bars;
   long long *sdoff, *sooff;
@@ -178,7 +180,10 @@ struct BlockGi
     scr = r + ne;
     hred = scr + 80; // 2 x 128 class sums of a Householder application (double-buffered) + the scaled dot
     rtri = hred + 264; // blocked R solve: RB x (R_kk, ~ 1 / R_kk, R_{k-1,k}, -)
-    Lt = rtri + 4 * RB;
+    MJ = (n + 127) / 128;
+    qring = rtri + 4 * RB; // [QD][MJ][128]
+    rtau = qring + QD * MJ * 128; // tau of record e (0 for a Givens record)
+    Lt = rtau + ((p.max_iter + 1) & ~1);
     Bt = Lt + p.G.nmax * p.G.nmax;
     ring = Bt + p.G.nmax * p.G.nmax + ((2 * p.G.nmax * p.G.nmax) & 1); // 16-byte aligned (bulk copies)
     dgp = reinterpret_cast<double2 *>(ring + (p.fast_nb ? ring_doubles(p.fast_nb) - RING * 32 : 0));
@@ -200,7 +205,8 @@ struct BlockGi
     const long long ne = (n + 2) & ~1;
     const long long tiles = 2LL * nmax * nmax + ((2LL * nmax * nmax) & 1);
     const long long fast = fast_nb ? ring_doubles(fast_nb) + RING + 2LL * b : 0;
-    return (6 * ne + 80 + 264 + 4 * RB + tiles + fast) * 8 + (3LL * max_iter + n + 16) * 4 + ((m + 15) & ~15);
+    const long long qst = (long long)QD * ((n + 127) / 128) * 128 + ((max_iter + 1) & ~1);
+    return (6 * ne + 80 + 264 + 4 * RB + qst + tiles + fast) * 8 + (3LL * max_iter + n + 16) * 4 + ((m + 15) & ~15);
   }
 
   // once per kernel: barriers of the ring, block offsets of G in shared memory (the solves read them on their critical path)
@@ -405,6 +411,39 @@ struct BlockGi
     }
   }
 
+  // the same with c (cs[0 .. size)) and s (cs[soff .. soff + size)) staged in shared memory: uniform loads, no shuffle
+  __device__ __forceinline__ void givens_record_staged(double * vs, const double * cs, const int soff, const int size, const int dir)
+  {
+    if(dir > 0)
+    {
+      double carry = vs[0];
+#pragma unroll 4
+      for(int i = 0; i < size; ++i)
+      {
+        const double c = cs[i], sn = cs[soff + i];
+        const double xi = carry, yi = vs[i + 1];
+        const double nx = fma(c, xi, -(sn * yi));
+        carry = fma(c, yi, sn * xi);
+        if(lane == 0) vs[i] = nx;
+      }
+      if(lane == 0) vs[size] = carry;
+    }
+    else
+    {
+      double carry = vs[size];
+#pragma unroll 4
+      for(int i = size - 1; i >= 0; --i)
+      {
+        const double c = cs[i], sn = cs[soff + i];
+        const double xi = vs[i], yi = carry;
+        carry = fma(c, xi, sn * yi);
+        const double ny = fma(c, yi, -(sn * xi));
+        if(lane == 0) vs[i + 1] = ny;
+      }
+      if(lane == 0) vs[0] = carry;
+    }
+  }
+
   // dir = +1: Q^T v (records in order of addition), dir = -1: Q v (reverse order)
   __device__ void apply_sequence_smem(double * v, const int dir)
   {
@@ -434,25 +473,66 @@ struct BlockGi
     __syncthreads();
   }
 
-  // reflector of record e for this thread (entry k of v belongs to thread k mod 128): pk[j] = E[tid + 128 j - start] inside
-  // [start, end), 1.0 for the implicit leading entry, 0 elsewhere; st: start (sign bit: a Givens record), en: one past the end
-  __device__ __forceinline__ void fetch_record(const int e, const int kt, double (&pk)[MAXE], double & tau, int & st, int & en) const
+  // The reflector of record e travels to the thread that uses it as cp.async copies into a thread-PRIVATE slot of a
+  // QD-deep stage (entry k of v belongs to thread k mod 128, so the thread that issues a copy is the only one that ever
+  // reads it: no barrier, no register held while the copy is in flight); entries outside [start, end) are zero-filled.
+  // One commit group per call (empty for a Givens record or past the end), so that wait_group<QD - 1> always means "the
+  // record about to be applied has landed".
+  __device__ __forceinline__ void issue_record(const int e, const bool valid, const int kt) const
+  {
+    if(valid)
+    {
+      const int s = rec[3 * e], en = s + rec[3 * e + 1];
+      if(s < 0 && warp == 0)
+      {
+        // a Givens record: c and s of its rotations, when they fit the slot (they are read by warp 0 after a barrier)
+        const int sz = rec[3 * e + 1];
+        if(sz <= MJ * 64)
+        {
+          const double * p = Qg + rec[3 * e + 2];
+          double * slot = qring + ((unsigned)e % QD) * MJ * 128;
+          for(int k = lane; k < sz; k += 32)
+          {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bg_smem_addr(slot + k)), "l"(p + k) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bg_smem_addr(slot + MJ * 64 + k)), "l"(p + sz + k) : "memory");
+          }
+        }
+      }
+      if(s >= 0 && tid < 128)
+      {
+        const double * p = Qg + rec[3 * e + 2];
+        double * slot = qring + ((unsigned)e % QD) * MJ * 128 + tid;
+#pragma unroll
+        for(int j = 0; j < MAXE; ++j)
+        {
+          if(j < MJ)
+          {
+            const int k = kt + 128 * j;
+            const bool in = k >= s && k < en;
+            const double * src = in ? p + (k - s) : p;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(bg_smem_addr(slot + 128 * j)), "l"(src), "r"(in ? 8 : 0) : "memory");
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // pk[j] = E[tid + 128 j - start] inside [start, end), 1.0 for the implicit leading entry, 0 elsewhere; st: start (sign
+  // bit: a Givens record), en: one past the end
+  __device__ __forceinline__ void take_record(const int e, const int kt, double (&pk)[MAXE], double & tau, int & st, int & en) const
   {
     const int s = rec[3 * e], sz = rec[3 * e + 1];
-    const double * p = Qg + rec[3 * e + 2];
     st = s;
     en = (s & 0x7fffffff) + sz;
-    tau = 0.0;
-    if(s >= 0) // (uniform)
-    {
-      tau = p[0];
+    tau = rtau[e];
+    asm volatile("cp.async.wait_group %0;" ::"n"(QD - 1) : "memory");
+    const double * slot = qring + ((unsigned)e % QD) * MJ * 128 + (tid & 127);
 #pragma unroll
-      for(int j = 0; j < MAXE; ++j)
-      {
-        const int k = kt + 128 * j;
-        const double t = (k >= s && k < en) ? p[k - s] : 0.0;
-        pk[j] = k == s ? 1.0 : t;
-      }
+    for(int j = 0; j < MAXE; ++j)
+    {
+      const double t = j < MJ ? slot[128 * j] : 0.0;
+      pk[j] = (kt + 128 * j) == s ? 1.0 : t;
     }
   }
 
@@ -505,7 +585,13 @@ struct BlockGi
         if(k >= s0 && k <= en) v[k] = vr[j];
       }
       __syncthreads();
-      if(warp == 0) givens_record(v + s0, Qg + rec[3 * e + 2], en - s0, dir);
+      if(warp == 0)
+      {
+        if(en - s0 <= MJ * 64)
+          givens_record_staged(v + s0, qring + ((unsigned)e % QD) * MJ * 128, MJ * 64, en - s0, dir);
+        else
+          givens_record(v + s0, Qg + rec[3 * e + 2], en - s0, dir);
+      }
       __syncthreads();
 #pragma unroll
       for(int j = 0; j < MAXE; ++j)
@@ -526,7 +612,7 @@ struct BlockGi
   // are pulled into L2 (the list of a config-E solve, ~ 0.4 MB per CTA, does not stay there: profiles/r02y_*).
   __device__ void apply_sequence_reg(double * v, const int dir)
   {
-    constexpr int PFD = 6; // records of look-ahead of the L2 prefetch
+    constexpr int PFD = 8; // records of look-ahead of the L2 prefetch
     if(nrec > 0)
     {
       const int kt = tid < 128 ? tid : 0x40000000; // (threads beyond the 128 classes own nothing)
@@ -537,29 +623,21 @@ struct BlockGi
         const int k = kt + 128 * j;
         vr[j] = k < n ? v[k] : 0.0;
       }
-      double pa[MAXE], pb[MAXE], ta, tb = 0.0;
-      int sa, ea, sb = 0, eb = 0;
-#pragma unroll
-      for(int j = 0; j < MAXE; ++j) pa[j] = pb[j] = 0.0;
+      double pc[MAXE], tc;
+      int sc, ec;
       int e = dir > 0 ? 0 : nrec - 1;
       for(int a = 1; a < PFD && a < nrec; ++a) prefetch_record_l2(e + dir * a);
-      fetch_record(e, kt, pa, ta, sa, ea);
+      for(int a = 0; a < QD - 1; ++a) issue_record(e + dir * a, a < nrec, kt);
       int buf = 0;
-      int left = nrec;
 #pragma unroll 1
-      for(;;)
+      for(int left = nrec; left > 0; --left, e += dir)
       {
         if(left > PFD) prefetch_record_l2(e + dir * PFD);
-        if(left > 1) fetch_record(e + dir, kt, pb, tb, sb, eb);
-        apply_record(e, dir, kt, v, vr, pa, ta, sa, ea, buf);
-        e += dir;
-        if(--left == 0) break;
-        if(left > PFD) prefetch_record_l2(e + dir * PFD);
-        if(left > 1) fetch_record(e + dir, kt, pa, ta, sa, ea);
-        apply_record(e, dir, kt, v, vr, pb, tb, sb, eb, buf);
-        e += dir;
-        if(--left == 0) break;
+        issue_record(e + dir * (QD - 1), left > QD - 1, kt);
+        take_record(e, kt, pc, tc, sc, ec);
+        apply_record(e, dir, kt, v, vr, pc, tc, sc, ec, buf);
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for(int j = 0; j < MAXE; ++j)
       {
@@ -651,15 +729,16 @@ struct BlockGi
   }
 
   // the whole block, uniform-pivot recurrence: per link one pair load (L_kk and its reciprocal, prepared a block ahead),
-  // three FMAs for the quotient, one for the next pivot, one for the lane's own row; straight-line code (selects, no
-  // branch). The quotients are PROVEN afterwards, link k by lane k (its pivot, its diagonal entry, its x_k); false: some
-  // proof failed, wr and xs are to be discarded.
+  // three FMAs for the quotient, one for the next pivot, one (predicated) for the lane's own row — straight-line code.
+  // A lane stops updating its row at its own link, so lane k is left holding ITS PIVOT: after the loop it forms its own
+  // quotient again (the same three FMAs on the same operands as the uniform copy: the same bits), PROVES it correctly
+  // rounded (fp64_exact.cuh) and keeps it as its entry of the solution. false: some proof failed, wr and xs are to be
+  // discarded.
   template<int NB, bool TR>
-  __device__ __forceinline__ bool block_solve_fast(const double * Ls, const double2 * dp, double & wr, const double dg, double (&xs)[NB])
+  __device__ __forceinline__ bool block_solve_fast(const double * Ls, const double2 * dp, double & wr, double (&xs)[NB])
   {
     constexpr int LDT = NB == 16 ? 18 : NB;
     const int lc = min(lane, NB - 1);
-    double wsave = 0.0;
     double wp = __shfl_sync(BG_FULL, wr, TR ? NB - 1 : 0);
 #pragma unroll
     for(int s = 0; s < NB; ++s)
@@ -671,15 +750,17 @@ struct BlockGi
       const double q0 = wp * dr.y;
       const double e = fma(-dr.x, q0, wp);
       const double xk = fma(e, dr.y, q0);
-      wsave = lane == k ? wp : wsave;
       xs[k] = xk;
       if(s + 1 < NB) wp = fma(-xk, TR ? Ls[k + kn * LDT] : Ls[kn + k * LDT], tn);
       const double lr = TR ? Ls[k + lc * LDT] : Ls[lc + k * LDT];
-      const double nw = fma(-xk, lr, wr);
-      const bool upd = TR ? lane < k : lane > k;
-      wr = lane == k ? xk : (upd ? nw : wr);
+      if(TR ? lane < k : lane > k) wr = fma(-xk, lr, wr);
     }
-    const bool ok = lane >= NB || div_proof(wsave, dg, wr);
+    const double2 own = dp[lc];
+    const double q0 = wr * own.y;
+    const double e = fma(-own.x, q0, wr);
+    const double xo = fma(e, own.y, q0);
+    const bool ok = lane >= NB || div_proof(wr, own.x, xo);
+    wr = xo;
     return __all_sync(BG_FULL, ok);
   }
 
@@ -714,17 +795,16 @@ struct BlockGi
         ring_issue<NB>(i, j == 0 ? -1 : (TR ? i : i - 1), j % RING);
       }
     };
-    // (L_kk, ~ 1 / L_kk) of the tile in stage `slot`, lane k the pair k; returns the lane's own L_kk
-    auto prepare = [&](int slot) -> double
+    // (L_kk, ~ 1 / L_kk) of the tile in stage `slot`, lane k the pair k
+    auto prepare = [&](int slot)
     {
       const double dgv = (ring + slot * 2 * TT)[lc + lc * LDT];
       if(lane < NB) dgp[slot * 16 + lane] = make_double2(dgv, bg_rcp(dgv));
-      return dgv;
     };
     __syncwarp();
     for(int j = 0; j < AHEAD && j < cnt; ++j) issue(j);
     ring_wait(0);
-    double dg = prepare(0);
+    prepare(0);
     double xs[NB];
 #pragma unroll
     for(int k = 0; k < NB; ++k) xs[k] = 0.0;
@@ -737,11 +817,10 @@ struct BlockGi
       const double * Ss = Ls + TT;
       __syncwarp(); // every lane is done with the stage of block j - 1, which the next copy overwrites; pairs of block j visible
       if(j + AHEAD < cnt) issue(j + AHEAD);
-      double dgn = 1.0;
       if(j + 1 < cnt)
       {
         ring_wait((j + 1) % RING);
-        dgn = prepare((j + 1) % RING);
+        prepare((j + 1) % RING);
       }
       double wr = v[i * NB + lc];
       if(j > 0)
@@ -769,7 +848,7 @@ struct BlockGi
       }
       const double w0 = wr;
       bool fast = klo == 0 && khi == NB;
-      if(fast) fast = block_solve_fast<NB, TR>(Ls, dgp + slot * 16, wr, dg, xs);
+      if(fast) fast = block_solve_fast<NB, TR>(Ls, dgp + slot * 16, wr, xs);
       if(!fast)
       {
         wr = block_solve_exact<NB, TR>(Ls, w0, klo, khi);
@@ -777,7 +856,6 @@ struct BlockGi
         for(int k = 0; k < NB; ++k) xs[k] = __shfl_sync(BG_FULL, wr, k);
       }
       if(lane < NB) v[i * NB + lane] = wr;
-      dg = dgn;
     }
   }
 
@@ -847,7 +925,7 @@ struct BlockGi
           if(lane < RB) reinterpret_cast<double4 *>(rtri)[lane] = make_double4(dg, bg_rcp(dg), sup, 0.0);
           const double4 * tri = reinterpret_cast<const double4 *>(rtri);
           __syncwarp();
-          double wj = w0, rv = 0.0, wsave = 0.0;
+          double wj = w0;
           double wp = __shfl_sync(BG_FULL, wj, nbk - 1);
 #pragma unroll
           for(int c = RB - 1; c >= 0; --c)
@@ -858,17 +936,19 @@ struct BlockGi
             const double q0 = wp * t4.y;
             const double e = fma(-t4.x, q0, wp);
             const double rk = fma(e, t4.y, q0);
-            wsave = (act && lane == c) ? wp : wsave;
-            rv = (act && lane == c) ? rk : rv;
             if(c > 0)
             {
               const double wn = fma(-rk, t4.z, tn);
               wp = act ? wn : wp;
             }
-            const double nw = fma(-rk, Tc[c], wj);
-            wj = (act && lane < c) ? nw : wj;
+            if(act && lane < c) wj = fma(-rk, Tc[c], wj); // (a lane stops at its own link: it is left holding its pivot)
           }
-          const bool ok = lane >= nbk || div_proof(wsave, dg, rv);
+          // lane c: its own quotient again (same operands, same bits) and the proof that it is correctly rounded
+          const double4 own = tri[min(lane, RB - 1)];
+          const double q0 = wj * own.y;
+          const double eo = fma(-own.x, q0, wj);
+          const double rv = fma(eo, own.y, q0);
+          const bool ok = lane >= nbk || div_proof(wj, own.x, rv);
           done = __all_sync(BG_FULL, ok);
           if(done && lane < nbk) r[k0 + lane] = rv;
           __syncwarp();
@@ -1065,6 +1145,7 @@ struct BlockGi
     {
       pe[0] = tau;
       Rq[q] = beta;
+      rtau[nrec] = tau;
       rec[3 * nrec] = q;
       rec[3 * nrec + 1] = len;
       rec[3 * nrec + 2] = (int)qoff;
@@ -1129,6 +1210,7 @@ struct BlockGi
     }
     if(tid == 0)
     {
+      rtau[nrec] = 0.0;
       rec[3 * nrec] = l | (int)0x80000000;
       rec[3 * nrec + 1] = g;
       rec[3 * nrec + 2] = (int)qoff;
@@ -1381,6 +1463,7 @@ __global__ void blockgi_sequence_test_kernel(const BlockGiParams P, const int * 
   extern __shared__ __align__(16) double sm[];
   BlockGi<8> S(P, sm);
   for(int i = threadIdx.x; i < 3 * nrec; i += blockDim.x) S.rec[i] = rec_in[i];
+  for(int i = threadIdx.x; i < nrec; i += blockDim.x) S.rtau[i] = rec_in[3 * i] >= 0 ? S.Qg[rec_in[3 * i + 2]] : 0.0;
   S.nrec = nrec;
   for(int cs = blockIdx.x; cs < ncases; cs += gridDim.x)
   {
