@@ -39,6 +39,10 @@ namespace jrlqp
 {
 
 #define JRLQP_FULL 0xffffffffu
+#ifndef JRLQP_DMMA_CHOL
+#  define JRLQP_DMMA_CHOL 1 // four-warp kernels: the inner products of the Cholesky over the columns left of the current 16-column
+                           // block on the FP64 tensor cores (mma.sync.m8n8k4.f64), bit-identical to the dot4 chains
+#endif
 #ifndef JRLQP_UNR_CHOL
 #  define JRLQP_UNR_CHOL 4
 #endif
@@ -73,6 +77,16 @@ namespace jrlqp
 #endif
 #ifndef JRLQP_ZPART_W1
 #  define JRLQP_ZPART_W1 1 // (+1.3 % at n = 50, profiles/r03a_ab_A.txt) W == 2: in the main iterations (short Givens chain, long back substitution) the z-dependent half of the step length runs on warp 1
+#endif
+#ifndef JRLQP_CHAIN_BF
+#  define JRLQP_CHAIN_BF 1 // W = 4: the links of the Givens recurrence below the last one the seeds predict on another branch of
+                          // makeGivens run in a branch-free loop (operands two links ahead, exact branch test accumulated and checked once)
+#endif
+#ifndef JRLQP_CHAIN_BF_MINW
+#  define JRLQP_CHAIN_BF_MINW 4 // (W = 3, register-capped: -1.2 %, profiles/r4i_ab_bf.txt; W = 2: profiles/r4k_ab_bf_w2.txt)
+#endif
+#ifndef JRLQP_CHAIN_BF_UNR
+#  define JRLQP_CHAIN_BF_UNR 2
 #endif
 #ifndef JRLQP_SEEDS_IN_Z
 #  define JRLQP_SEEDS_IN_Z 1 // (+1.6 % at n = 50, neutral at n = 128, profiles/r03b_ab_*.txt) W > 1: the seeds of the Givens recurrence are computed by ALL the threads next to z = J2 d2 (one element each)
@@ -876,15 +890,81 @@ struct GiCta
     // --- left-looking Cholesky, thread = row
     {
       const double * Li = Jb + ic * ldj;
+      // DMMA (W = 4): at the first column of every 8-column panel the four dot4 accumulators of all the entries of the panel
+      // are advanced over the columns j < K0 = 16 floor(k / 16) by mma.sync.m8n8k4.f64 — one DMMA is the sequential chain
+      // fma(a3,b3, fma(a2,b2, fma(a1,b1, fma(a0,b0,c)))) bit for bit (profiles/r02t_dmma_probe.txt), so an accumulator tile fed
+      // with j = jb + t, jb + t + 4, jb + t + 8, jb + t + 12 IS chain t of the canonical dot4 — and parked in the (still
+      // unused) storage of R; the column loop below then starts its chains from them at j = K0 (<= 15 scalar terms per
+      // entry instead of up to n - 1). Rows of a warp are produced and consumed by that warp: no block barrier.
+      constexpr bool DMMA = W == 4 && JRLQP_DMMA_CHOL != 0;
+      constexpr int ACS = 33; // doubles per row of the parked accumulators: [column of the panel][chain] + 1 (odd: conflict-free)
+      double * const acs = Rp;
+      const bool dmma_on = DMMA && (long long)(32 * W) * ACS <= (long long)n * (n + 1) / 2;
 #pragma unroll 1
       for(int k = 0; k < n; ++k)
       {
+        int K0 = 0;
+        if(DMMA && dmma_on)
+        {
+          K0 = (k >> 4) << 4;
+          if((k & 7) == 0 && K0 > 0 && 32 * warp + 31 >= k)
+          {
+            const int g = lane >> 2, t = lane & 3; // fragments: A(row g, k t), B(k t, column g), C(row g, columns 2 t, 2 t + 1)
+            double acc[4][4][2];
+#pragma unroll
+            for(int rt = 0; rt < 4; ++rt)
+#pragma unroll
+              for(int ch = 0; ch < 4; ++ch) acc[rt][ch][0] = acc[rt][ch][1] = 0.0;
+            const double * Bp = Jb + min(k + g, n - 1) * ldj + 4 * t;
+            const double * Ap = Jb + min(32 * warp + g, n - 1) * ldj + 4 * t;
+            const int rstep = 8 * ldj;
+            const bool r1 = 32 * warp + 8 + g < n, r2 = 32 * warp + 16 + g < n, r3 = 32 * warp + 24 + g < n; // (rows past n - 1: row of tile 0 again)
+#pragma unroll 1
+            for(int jb = 0; jb < K0; jb += 16)
+            {
+#pragma unroll
+              for(int ch = 0; ch < 4; ++ch)
+              {
+                const double bf = Bp[jb + ch];
+                const double a0f = Ap[jb + ch];
+                const double a1f = Ap[(r1 ? rstep : 0) + jb + ch];
+                const double a2f = Ap[(r2 ? 2 * rstep : 0) + jb + ch];
+                const double a3f = Ap[(r3 ? 3 * rstep : 0) + jb + ch];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[0][ch][0]), "+d"(acc[0][ch][1]) : "d"(a0f), "d"(bf));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[1][ch][0]), "+d"(acc[1][ch][1]) : "d"(a1f), "d"(bf));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[2][ch][0]), "+d"(acc[2][ch][1]) : "d"(a2f), "d"(bf));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[3][ch][0]), "+d"(acc[3][ch][1]) : "d"(a3f), "d"(bf));
+              }
+            }
+#pragma unroll
+            for(int rt = 0; rt < 4; ++rt)
+            {
+              double * o = acs + (32 * warp + 8 * rt + g) * ACS + 8 * t;
+#pragma unroll
+              for(int ch = 0; ch < 4; ++ch)
+              {
+                o[ch] = acc[rt][ch][0]; // column 2 t of the panel
+                o[4 + ch] = acc[rt][ch][1]; // column 2 t + 1
+              }
+            }
+            __syncwarp();
+          }
+        }
         double v = 0.0;
         if(32 * warp + 31 >= k) // warps entirely above the pivot row have nothing to do
         {
           const double * Lk = Jb + k * ldj;
           double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
           int j = 0;
+          if(DMMA && K0 > 0)
+          {
+            const double * o = acs + tid * ACS + 4 * (k & 7);
+            a0 = o[0];
+            a1 = o[1];
+            a2 = o[2];
+            a3 = o[3];
+            j = K0;
+          }
 #pragma unroll UNR_CHOL
           for(; j + 3 < k; j += 4)
           {
@@ -1910,6 +1990,14 @@ struct GiCta
       const double t = ds[j - 1] * rsd; // (j == 0: an unused read of the padding before d)
       const double ss = fma(t, t, 1.0);
       const double ysd = rsqrt_seed(ss);
+      if(W >= JRLQP_CHAIN_BF_MINW && JRLQP_CHAIN_BF)
+      {
+        // link j - 1 is PREDICTED off the fast branch of makeGivens (|p| <= |rho|, p != 0) when the seeds say |p / rho| is
+        // not safely below 1; the recurrence runs branch-free below the lowest such link (and checks the exact test there)
+        const bool ps = j > q && j < n && (!(fabs(t) <= 0.99999) || ds[j - 1] == 0.0);
+        const unsigned mk = __ballot_sync(JRLQP_FULL, ps);
+        if(lane == 0) reinterpret_cast<int *>(scr + 6)[warp] = mk ? 32 * warp + __ffs(mk) - 2 : JRLQP_NONE;
+      }
       if(j >= q && j < n)
       {
         if(j > q)
@@ -2086,6 +2174,16 @@ struct GiCta
       __syncwarp();
     }
     bool careful = false;
+    constexpr bool WIDE_BF = W >= JRLQP_CHAIN_BF_MINW && SEEDS_IN_Z && JRLQP_CHAIN_BF != 0;
+    constexpr int BF_UNR = JRLQP_CHAIN_BF_UNR;
+    int jclean = JRLQP_NONE; // every link below this one is predicted on the fast branch of makeGivens
+    if(WIDE_BF)
+    {
+      const int * jc = reinterpret_cast<const int *>(scr + 6);
+      jclean = jc[0];
+#pragma unroll
+      for(int w = 1; w < W; ++w) jclean = min(jclean, jc[w]);
+    }
 #pragma unroll 1
     for(;;)
     {
@@ -2097,8 +2195,9 @@ struct GiCta
       double2 sd = pr[0]; // (~ 1 / rho, ~ u)
       double hh = pr[1].x; // ~ 1 / (2 u)
       double q0s = p * sd.x; // first product of the quotient p / rho, issued ahead
+      const int ia = (WIDE_BF && !careful) ? max(q, jclean) : q; // the links i >= ia keep the branch
 #pragma unroll CHAIN_UNR
-      for(; i >= q; --i)
+      for(; i >= ia; --i)
       {
         // operands of the next link (i == 0: unused reads of the padding)
         const double pn = pd[-1];
@@ -2150,6 +2249,50 @@ struct GiCta
         q0s = pn * sn.x;
         --pd;
         pr -= 2;
+      }
+      if(WIDE_BF)
+      {
+        // ---- the links predicted on the fast branch: the same six operations, no branch; the operands are loaded two
+        //      links ahead so that the first product of the next quotient is ready when its link starts
+        bool bad = false;
+        double pn = pd[-1];
+        double2 sn = pr[-2];
+        double hn = pr[-1].x;
+#pragma unroll BF_UNR
+        for(; i >= q; --i)
+        {
+          const double p2 = pd[-2]; // (reads below link q: addressable shared memory, values unused)
+          const double2 s2 = pr[-4];
+          const double h2 = pr[-3].x;
+          const double q0n = pn * sn.x;
+          const double e3 = fma(-rho, q0s, p);
+          const double a = fma(e3, sd.x, q0s);
+          const double s = fma(a, a, 1.0);
+          const double rem = fma(-sd.y, sd.y, s);
+          const double us = fma(rem, hh, sd.y);
+          const double r = fabs(rho) * us;
+          const double u = __hiloint2double(__double2hiint(us) | (__double2hiint(rho) & 0x80000000), __double2loint(us));
+          bad = bad || !(fabs(p) <= fabs(rho)) || p == 0.0;
+          pr[0] = make_double2(a, u);
+          pr[1].x = rho;
+          rho = r;
+          p = pn;
+          sd = sn;
+          hh = hn;
+          q0s = q0n;
+          pn = p2;
+          sn = s2;
+          hn = h2;
+          --pd;
+          pr -= 2;
+        }
+        if(bad)
+        {
+          // a link the seeds had predicted on the fast branch was not (never seen; the seeds are accurate to ~ 2^-40 and the
+          // prediction keeps a margin of 1e-5): the chain again, every link taken literally (the seeds are overwritten)
+          careful = true;
+          continue;
+        }
       }
       scr[10] = rho;
       __syncwarp();
