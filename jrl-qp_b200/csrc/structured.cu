@@ -359,6 +359,29 @@ int jrlqp_structured_solve_device(jrlqp_structured * s,
   p.transpose = transpose ? 1 : 0;
   p.hint_start = start;
   p.hint_end = end;
+  // small uniform tiles: one column per warp, solved in place, tiles streamed by TMA (structured_small.cuh); needs 16-byte
+  // aligned instances (the offsets inside one are even)
+  const bool aligned = (reinterpret_cast<uintptr_t>(data) % 16) == 0 && (stride % 2) == 0;
+  const int mode = s->kernel_mode == 0 ? (s->small_nb && aligned ? 3 : 1) : s->kernel_mode;
+  if(mode >= 2 && s->small_nb && aligned)
+  {
+    const int nb = s->small_nb;
+    void (*fn)(const StructParams) = nb == 8 ? structured_solve_small_kernel<8> : (nb == 12 ? structured_solve_small_kernel<12> : structured_solve_small_kernel<16>);
+    const long long per_warp = TriWarp::ring_doubles(nb) + TriWarp::RING + (TriWarp::RING & 1);
+    const int smem = (int)((2LL * s->b + 4 * per_warp) * 8);
+    SCK(jrlqp::raise_smem_limit(fn, smem));
+    int occ = 0;
+    SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, smem));
+    if(occ >= 1)
+    {
+      const long long work = batch * ncols;
+      const long long grid = std::min<long long>((work + 3) / 4, (long long)occ * s->num_sms);
+      fn<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(p);
+      count_launch();
+      SCK(cudaGetLastError());
+      return JRLQP_OK;
+    }
+  }
   const long long grid = std::min<long long>(batch * ncols, (long long)s->solve_occ * s->num_sms);
   structured_solve_kernel<<<(unsigned)grid, s->threads, s->solve_smem, (cudaStream_t)stream>>>(p);
   count_launch();

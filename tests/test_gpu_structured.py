@@ -157,6 +157,36 @@ def test_small_tile_llt_kernels_bit_exact(kernel, size, blocks, batch):
     assert np.array_equal(g.solveL(V.copy())[good], ref[good])
 
 
+@pytest.mark.parametrize("kernel", [1, 3])
+@pytest.mark.parametrize("size,blocks", [(12, 6), (8, 5), (16, 4), (12, 1)])
+def test_small_tile_solve_kernel_hint_windows(kernel, size, blocks):
+    """The batch solves of chains of uniform dense tiles (round 2: one column per warp, in place, uniform-pivot recurrence
+    with proven quotients, tiles by TMA bulk copies: structured_solve_small_kernel) against the oracle, bit for bit: both
+    directions, several columns per instance, and (start, end) hint windows that begin / end in the middle of a tile, on a
+    tile boundary and at the ends — beside the general kernel (1) on the same inputs."""
+    sizes = [size] * blocks
+    n = size * blocks
+    st = Structure.packed(Type.TriBlockDiagonal, sizes)
+    batch = 37
+    H = sc.make_H(Type.TriBlockDiagonal, sizes, batch, seed=11 + size, shift=1.0)
+    g, ok, data_ref, ok_ref = _factor_both(st, H, kernel)
+    assert ok.all() and np.array_equal(g.data, data_ref)
+    rng = np.random.default_rng(4)
+    wins = {(0, n), (0, 1), (n - 1, n), (size // 2, n), (0, n - size // 2), (size, n), (0, size)}
+    if blocks > 2:
+        wins |= {(size + 3, 2 * size + 5), (2 * size, 3 * size), (size - 1, size + 1), (2 * size - 1, n - 1)}
+    before = S.launch_count()
+    for (i, j) in sorted(wins):
+        for ncols in (1, 3):
+            V = np.zeros((batch, ncols, n))
+            V[:, :, i:j] = rng.uniform(-1, 1, (batch, ncols, j - i))
+            for transpose in (False, True):
+                ref = po.decomp_solve(st, data_ref, V.copy(), transpose=transpose, start=i, end=j, nthreads=os.cpu_count())
+                out = g.solveLTranspose(V.copy(), i, j) if transpose else g.solveL(V.copy(), i, j)
+                assert np.array_equal(out, ref), (kernel, size, blocks, i, j, ncols, transpose)
+    assert S.launch_count() > before
+
+
 def test_small_tile_kernel_refused_on_other_structures():
     st = Structure.packed(Type.BlockArrowDown, [12] * 4)
     g = StructuredG(st, st.pack(sc.make_H(Type.BlockArrowDown, [12] * 4, 2, seed=1, shift=1.0)))
