@@ -143,7 +143,9 @@ struct BlockGi
   int q, nrec;
   long long qoff;
   double f;
-  TriWarp tw; // warp 0: the structured solves
+  TriWarp tw; // the serial warp: the structured solves
+  int sw; // the warp that runs the serial parts (solves, Givens records, R solve): rotated over the CTAs of an SM, whose
+          // warps 0 would otherwise all sit on the same scheduler while the three others idle
 
   static __host__ __device__ long long ring_doubles(int nb) { return TriWarp::ring_doubles(nb); }
 
@@ -178,6 +180,9 @@ struct BlockGi
     double * slot = p.ws + (long long)blockIdx.x * p.ws_stride;
     Rg = slot;
     Qg = slot + (long long)n * (n + 1) / 2;
+    unsigned nsm;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    sw = (int)((blockIdx.x / max(1u, nsm)) % (unsigned)(blockDim.x >> 5));
     tw.ring = ring;
     tw.dgp = dgp;
     tw.bars = bars;
@@ -461,7 +466,7 @@ struct BlockGi
 
   // The reflector of record e travels to the thread that uses it as cp.async copies into a thread-PRIVATE slot of a
   // QD-deep stage (entry k of v belongs to thread k mod 128, so the thread that issues a copy is the only one that ever
-  // reads it: no barrier, no register held while the copy is in flight); entries outside [start, end) are zero-filled.
+  // reads it: no barrier, no register held while the copy is in flight); entries outside [start, end) are not copied.
   // One commit group per call (empty for a Givens record or past the end), so that wait_group<QD - 1> always means "the
   // record about to be applied has landed".
   __device__ __forceinline__ void issue_record(const int e, const bool valid, const int kt) const
@@ -469,7 +474,7 @@ struct BlockGi
     if(valid)
     {
       const int s = rec[3 * e], en = s + rec[3 * e + 1];
-      if(s < 0 && warp == 0)
+      if(s < 0 && warp == sw)
       {
         // a Givens record: c and s of its rotations, when they fit the slot (they are read by warp 0 after a barrier)
         const int sz = rec[3 * e + 1];
@@ -494,9 +499,7 @@ struct BlockGi
           if(j < MJ)
           {
             const int k = kt + 128 * j;
-            const bool in = k >= s && k < en;
-            const double * src = in ? p + (k - s) : p;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(bg_smem_addr(slot + 128 * j)), "l"(src), "r"(in ? 8 : 0) : "memory");
+            if(k >= s && k < en) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bg_smem_addr(slot + 128 * j)), "l"(p + (k - s)) : "memory");
           }
         }
       }
@@ -517,8 +520,9 @@ struct BlockGi
 #pragma unroll
     for(int j = 0; j < MAXE; ++j)
     {
-      const double t = j < MJ ? slot[128 * j] : 0.0;
-      pk[j] = (kt + 128 * j) == s ? 1.0 : t;
+      const int k = kt + 128 * j;
+      const double t = (j < MJ && k > s && k < en) ? slot[128 * j] : 0.0; // (entries outside the record were not copied)
+      pk[j] = k == s ? 1.0 : t;
     }
   }
 
@@ -571,7 +575,7 @@ struct BlockGi
         if(k >= s0 && k <= en) v[k] = vr[j];
       }
       __syncthreads();
-      if(warp == 0)
+      if(warp == sw)
       {
         if(en - s0 <= MJ * 64)
           givens_record_staged(v + s0, qring + ((unsigned)e % QD) * MJ * 128, MJ * 64, en - s0, dir);
@@ -649,30 +653,32 @@ struct BlockGi
   {
     if(P.fast_nb && (P.flags & BGF_WARP_SOLVE))
     {
-      if(warp == 0)
+      if(warp == sw)
       {
-        tw.base = base;
+        TriWarp t = tw; // (a local copy: its address, not the solver's, is what the out-of-line exact path sees)
+        t.base = base;
         if(P.fast_nb == 8)
         {
           if(transpose)
-            tw.solve<8, true>(v, start, end);
+            t.solve<8, true>(v, start, end);
           else
-            tw.solve<8, false>(v, start, end);
+            t.solve<8, false>(v, start, end);
         }
         else if(P.fast_nb == 12)
         {
           if(transpose)
-            tw.solve<12, true>(v, start, end);
+            t.solve<12, true>(v, start, end);
           else
-            tw.solve<12, false>(v, start, end);
+            t.solve<12, false>(v, start, end);
         }
         else
         {
           if(transpose)
-            tw.solve<16, true>(v, start, end);
+            t.solve<16, true>(v, start, end);
           else
-            tw.solve<16, false>(v, start, end);
+            t.solve<16, false>(v, start, end);
         }
+        tw.rph = t.rph;
       }
       __syncthreads();
     }
@@ -690,7 +696,7 @@ struct BlockGi
     for(int k1 = q; k1 > 0; k1 -= RB)
     {
       const int k0 = max(0, k1 - RB), nbk = k1 - k0;
-      if(warp == 0)
+      if(warp == sw)
       {
         const int lc = min(lane, nbk - 1);
         const double w0 = w[k0 + lc];
