@@ -19,6 +19,7 @@ using namespace jrlqp;
 namespace
 {
 
+static int g_seq_fcache = 1; // JRLQP_SEQ_FCACHE=0: every step of a warm-started sequence factorises again (A/B, tests)
 static int g_zero_copy_G = -1; // kernels read G from the caller's pinned host buffer: 1 on, 0 off, -1 automatic (n <= 64); JRLQP_G_ZEROCOPY
 static bool g_h2d_lower = true; // host entry points upload only what the kernels read of G (see h2d_G)
 std::atomic<long long> g_launches{0};
@@ -162,6 +163,9 @@ struct jrlqp_solver
   int wocc = 0;
   signed char * d_as = nullptr; // staging of as_in for the host entry point
   // warm-started sequences (jrlqp_solve_sequence_*): scratch for per-step iterations / status and host staging
+  double * d_fcache = nullptr; // factor of step 0 of a warm-started sequence (gi_params.h: fcache), re-read by the later steps
+  long long fcache_cap = 0; // doubles
+  int fcache_mode = 0; // mode of the next launch (set by sequence_device_impl only)
   int * d_seq_it = nullptr;
   int * d_seq_status = nullptr;
   long long cap_seq = 0;
@@ -413,6 +417,10 @@ int jrlqp_create(jrlqp_solver ** out, int32_t n, int32_t mc, int32_t use_bounds,
     s->err = "this library contains sm_100a code only (Blackwell B200 required)";
     return JRLQP_ERR_CUDA;
   }
+  {
+    const char * e = getenv("JRLQP_SEQ_FCACHE");
+    g_seq_fcache = e ? e[0] != '0' : 1;
+  }
   if(const char * e = getenv("JRLQP_G_ZEROCOPY")) g_zero_copy_G = e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1);
   if(const char * e = getenv("JRLQP_H2D_FULL_G")) g_h2d_lower = !(e[0] == '1'); // tuning comparison: upload all of G
   s->num_sms = prop.multiProcessorCount;
@@ -433,7 +441,7 @@ int jrlqp_destroy(jrlqp_solver * s)
 {
   if(!s) return JRLQP_OK;
   cudaSetDevice(s->device);
-  void * ptrs[] = {s->d_cts, s->d_pre, s->d_pre_ok, s->d_ct, s->d_ct_busy, s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
+  void * ptrs[] = {s->d_fcache, s->d_cts, s->d_pre, s->d_pre_ok, s->d_ct, s->d_ct_busy, s->d_seq_it, s->d_seq_status, s->d_seq, s->d_seq_tot, s->d_work[0], s->d_work[1], s->d_busy[0], s->d_busy[1], s->d_as, s->d_phase, s->d_counters, s->d_G, s->d_a, s->d_C, s->d_bl, s->d_bu, s->d_xl, s->d_xu, s->d_x, s->d_u, s->d_f, s->d_L,
                    s->d_it, s->d_status, s->d_alist, s->d_nact, s->d_act};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -712,6 +720,9 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
   p.off_bact = lay.off_bact;
   p.off_hco = lay.off_hco;
   p.off_alpha = lay.off_alpha;
+  p.fcache = s->d_fcache;
+  p.fcache_stride = (long long)s->n * s->n + 2ll * s->n;
+  p.fcache_mode = (warm && !s->large && s->d_fcache != nullptr) ? s->fcache_mode : 0;
   const int occ = s->large ? s->locc[warm ? 1 : 0] : (warm ? s->wocc : s->occ);
   long long grid = std::min<long long>((long long)occ * s->num_sms, std::max<long long>(pb->batch, 1));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
@@ -941,6 +952,11 @@ static int solve_batch_host_impl(jrlqp_solver * s, const jrlqp_problem * pb, con
   const long long per_qp_bytes = 8 * (n * n + n + mc * n + 2 * mc + 2 * s->nb);
   long long chunk = std::max<long long>((long long)s->occ * s->num_sms * 4, (48ll << 20) / std::max<long long>(per_qp_bytes, 1));
   long long nchunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (B + chunk - 1) / chunk));
+  if(const char * e = getenv("JRLQP_HOST_CHUNK")) // tuning: QPs per chunk of the host pipeline (scripts/e2e_chunk_sweep.py)
+  {
+    const long long v = atoll(e);
+    if(v > 0) nchunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (B + v - 1) / v));
+  }
   chunk = (B + nchunks - 1) / nchunks;
 
   // arrays shared by the batch (stride 0): uploaded once, on stream 0; the other streams wait for them
@@ -1143,9 +1159,26 @@ static int sequence_device_impl(jrlqp_solver * s, const jrlqp_problem * pb, cons
     CK(cudaMalloc(&s->d_seq_status, sizeof(int) * (size_t)B));
     s->cap_seq = B;
   }
+  // G is the same at every step: the warm kernels keep the factor of step 0 in HBM and re-read it afterwards (same bits)
+  const bool use_fcache = seq->warm != 0 && !s->large && seq->steps > 1 && !res->L && g_seq_fcache != 0;
+  if(use_fcache)
+  {
+    const long long need = B * ((long long)s->n * s->n + 2ll * s->n);
+    if(need > s->fcache_cap)
+    {
+      if(s->d_fcache) CK(cudaFree(s->d_fcache));
+      s->d_fcache = nullptr;
+      s->fcache_cap = 0;
+      if(cudaMalloc(&s->d_fcache, sizeof(double) * (size_t)need) == cudaSuccess)
+        s->fcache_cap = need;
+      else
+        cudaGetLastError(); // (no room: the steps factorise again, as before)
+    }
+  }
   unsigned long long * counter = s->d_counters + (s->next_counter++ % kMaxChunks);
   for(int t = 0; t < seq->steps; ++t)
   {
+    s->fcache_mode = (use_fcache && s->d_fcache != nullptr && B * ((long long)s->n * s->n + 2ll * s->n) <= s->fcache_cap) ? (t == 0 ? 1 : 2) : 0;
     jrlqp_problem p = *pb;
     p.a = pb->a + (long long)t * seq->a_step_stride;
     jrlqp_result r = *res;
@@ -1167,6 +1200,7 @@ static int sequence_device_impl(jrlqp_solver * s, const jrlqp_problem * pb, cons
       p.as_stride = s->m;
     }
     int rc = launch(s, &p, &r, st, counter, seq->warm != 0, seq->warm != 0, /*pre_ready=*/t > 0);
+    s->fcache_mode = 0;
     if(rc != JRLQP_OK) return rc;
     if(totals)
     {

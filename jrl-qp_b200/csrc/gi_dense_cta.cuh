@@ -1339,9 +1339,34 @@ struct GiCta
     const int i = tid;
     const int ic = min(i, n - 1);
 
-    int st = warm_active_set(b);
-    if(st != TS_SUCCESS) return st;
+    // ---- sequences: the factor of an earlier step (same G, hence the same bits) comes back from HBM. The slot of diag(L)[0]
+    //      doubles as the state of the entry: > 0 (or NaN) a factor, < 0 G is not positive definite, 0 nothing stored yet
+    double * const fc = P.fcache_mode != 0 ? P.fcache + b * P.fcache_stride : nullptr;
+    const double fstate = P.fcache_mode == 2 ? fc[(long long)n * n] : 0.0; // (uniform)
 
+    int st = warm_active_set(b);
+    if(st != TS_SUCCESS)
+    {
+      if(P.fcache_mode == 1 && tid == 0) fc[(long long)n * n] = 0.0; // this step stores nothing: a later one factorises
+      return st;
+    }
+
+    const bool fload = fstate != 0.0;
+    if(fload)
+    {
+      if(fstate < 0.0) return TS_NON_POS_HESSIAN;
+#pragma unroll 4
+      for(int j = 0; j < n; ++j)
+        if(i < n) Jb[i * ldj + j] = fc[i + (long long)j * n];
+      if(i < n)
+      {
+        ldiag[i] = fc[(long long)n * n + i];
+        rs[i] = fc[(long long)n * n + n + i];
+      }
+      sync();
+    }
+    if(!fload)
+    {
     // ---- Cholesky (same code path and order as init())
 #pragma unroll 4
     for(int j = 0; j < n; ++j)
@@ -1374,7 +1399,11 @@ struct GiCta
         }
         sync();
         double vk = scr[0];
-        if(vk <= 0.0) return TS_NON_POS_HESSIAN;
+        if(vk <= 0.0)
+        {
+          if(fc != nullptr && tid == 0) fc[(long long)n * n] = -1.0;
+          return TS_NON_POS_HESSIAN;
+        }
         double lkk = sqrt(vk);
         if(i == k)
         {
@@ -1420,6 +1449,19 @@ struct GiCta
       }
     }
     sync();
+    if(fc != nullptr)
+    {
+      // step 0 of a sequence: keep the factor for the steps that follow
+#pragma unroll 4
+      for(int j = 0; j < n; ++j)
+        if(i < n) fc[i + (long long)j * n] = Jb[i * ldj + j];
+      if(i < n)
+      {
+        fc[(long long)n * n + i] = ldiag[i];
+        fc[(long long)n * n + n + i] = rs[i];
+      }
+    }
+    } // (!fload)
 
     // ---- active normals and b_act (initializeComputationData, :383-418), then B = L^-1 N,
     //      thread = active column k

@@ -83,6 +83,13 @@ struct GiParams
   int * ct_busy;
   int ct_slots;
   int ldct;
+  // warm-started sequences (jrlqp_solve_sequence_*): G does not change from step to step, so the factor of step 0 — L below the
+  // diagonal, J = L^-T above it, diag(L) and its reciprocals: n n + 2 n doubles per instance — is kept in HBM and re-read by the
+  // later steps instead of being recomputed (fcache_mode 0: off, 1: compute and store, 2: load). diag(L)[0] = -1 marks an
+  // instance whose G is not positive definite.
+  double * fcache;
+  long long fcache_stride;
+  int fcache_mode;
   // persistent work queue
   unsigned long long * counter;
   unsigned long long * phase_cycles; // [4 warps][16 phases], only with -DJRLQP_PHASE_TIMING (else null)

@@ -105,3 +105,72 @@ def test_sequence_device_pointers_shared_matrices():
     assert np.array_equal(act.cpu().numpy(), ref[-1]["active_set"])
     assert np.array_equal(tot.cpu().numpy(), sum(r["iterations"] for r in ref))
     assert int(worst.max()) == 0
+
+
+def _seq_with_env(value, fn):
+    old = os.environ.get("JRLQP_SEQ_FCACHE")
+    os.environ["JRLQP_SEQ_FCACHE"] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("JRLQP_SEQ_FCACHE")
+        else:
+            os.environ["JRLQP_SEQ_FCACHE"] = old
+
+
+def test_sequence_factor_cache_is_invisible():
+    """The steps t > 0 of a warm sequence re-read the factor step 0 stored in HBM (same G, same bits) instead of
+    factorising again: every output of every step is identical with the cache on and off (JRLQP_SEQ_FCACHE is read
+    when a handle is created), also after the handle has been used for a larger and a smaller batch."""
+    pb = P.random_problems(P.config_A(), 192, seed=11)
+    a_seq = _trajectory(pb, 7, 13)
+
+    def run():
+        sv = S.BatchedGoldfarbIdnaniSolver(pb.n, pb.mc, True, 192)
+        out = []
+        for nb in (64, 192, 100):  # grow, then shrink: the cache is sized by the largest call
+            sl = slice(0, nb)
+            sv.solve_sequence(pb.G[sl], a_seq[:, sl], pb.C[sl], pb.bl[sl], pb.bu[sl], pb.xl[sl], pb.xu[sl], warm=True, keep_steps=True)
+            out.append({k: np.array(v, copy=True) for k, v in sv.last.items() if isinstance(v, np.ndarray)})
+        return out
+
+    on = _seq_with_env("1", run)
+    off = _seq_with_env("0", run)
+    for a, b in zip(on, off):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+    ref = _oracle_sequence(pb, a_seq, True)
+    for t in range(a_seq.shape[0]):
+        assert np.array_equal(on[1]["x"][t], ref[t]["x"]) and np.array_equal(on[1]["iterations"][t], ref[t]["iterations"])
+
+
+def test_sequence_factor_cache_failed_first_step_and_indefinite_G():
+    """Instances whose step 0 stops before the factorisation (a guess with more than n equalities: OVERCONSTRAINED) store
+    nothing and factorise at the first step that gets that far; an indefinite G is remembered as such."""
+    ch = P.ProblemCharacteristics(8, 2, 10, nStrongActIneq=2, bounds=True, nStrongActBounds=1)
+    pb = P.random_problems(ch, 48, seed=5)
+    T = 5
+    a_seq = _trajectory(pb, T, 3)
+    m = pb.mc + pb.n
+    as0 = np.zeros((48, m), dtype=np.int8)
+    as0[::3, :pb.mc] = 3  # twelve EQUALITY guesses on eight variables
+    G = pb.G.copy()
+    G[1::7] = -G[1::7]  # not positive definite
+    sv = S.BatchedGoldfarbIdnaniSolver(pb.n, pb.mc, True, 48)
+    sv.solve_sequence(G, a_seq, pb.C, pb.bl, pb.bu, pb.xl, pb.xu, warm=True, as_in=as0, keep_steps=True)
+    g = sv.last
+    prev = as0
+    for t in range(T):
+        r = po.solve_batch(G, a_seq[t], pb.C, pb.bl, pb.bu, pb.xl, pb.xu, nthreads=os.cpu_count(), experimental=True,
+                           warm_start=True, as_in=prev)
+        assert np.array_equal(g["status"][t], r["status"]), f"step {t}"
+        ok = r["status"] == 0
+        for k in ("x", "u", "f", "iterations"):
+            assert np.array_equal(g[k][t][ok], r[k][ok]), f"step {t}: {k}"
+        prev = np.where(ok[:, None], r["active_set"], 0).astype(np.int8)  # a failed solve hands over an empty set (write_failure)
+        if t == 0:
+            assert (r["status"][::3] == 6).all() and (r["status"][1::7][np.arange(1, 48, 7) % 3 != 0] == 2).all()
+        else:
+            assert ok[[i for i in range(48) if i % 7 != 1]].all()
