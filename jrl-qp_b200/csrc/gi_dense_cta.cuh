@@ -707,6 +707,9 @@ struct GiCta
 #ifndef JRLQP_OPT_RS
 #  define JRLQP_OPT_RS 1
 #endif
+#ifndef JRLQP_QR4
+#  define JRLQP_QR4 1 // warm start: the Householder QR of the active normals updates its trailing columns with four lanes per column
+#endif
 #ifndef JRLQP_OPT_V2
 #  define JRLQP_OPT_V2 1
 #endif
@@ -1557,7 +1560,55 @@ struct GiCta
         rinv[k] = 1.0 / beta;
       }
       sync();
-      // apply H_k to the columns j > k, thread = column
+      // apply H_k to the columns j > k. JRLQP_QR4: FOUR lanes per column — lane c of a group runs chain c of the canonical dot4
+      // (the entries t = c, c + 4, ... of the column, ascending), the chains are folded (a0 + a1) + (a2 + a3) by two shuffles
+      // (additions commute: same bits), and the lane then updates the very entries it read — T / 4 columns per round instead of
+      // one column per thread with at most q - k - 1 of the T threads busy. Same operations per entry, same order: same bits.
+#if JRLQP_QR4
+      if(len == 0)
+      {
+        for(int j = k + 1 + tid; j < q; j += T)
+        {
+          double * top = Rp + colR(j) + k;
+          *top = *top * (1.0 - tau);
+        }
+      }
+      else if(tau != 0.0)
+      {
+        const int c = tid & 3;
+#pragma unroll 1
+        for(int j0 = k + 1; j0 < q; j0 += T / 4) // (uniform trip count: the shuffles below are executed by every lane)
+        {
+          const int j = j0 + (tid >> 2);
+          const bool on = j < q;
+          const int jc = on ? j : q - 1;
+          // rows k + 1 + t <= jc of column jc live in the packed upper storage, the rows below in the packed lower one
+          const double * up = Rp + colR(jc) + k + 1;
+          const double * lo = Vp + offV(jc) - (jc - k);
+          const int nup = jc - k; // entries t < nup are in the upper storage
+          double a = 0.0;
+          for(int t = c; t < len; t += 4) a = fma(ess[t], t < nup ? up[t] : lo[t], a);
+          double * top = Rp + colR(jc) + k;
+          const double tp = *top;
+          a = a + __shfl_xor_sync(JRLQP_FULL, a, 1);
+          a = a + __shfl_xor_sync(JRLQP_FULL, a, 2);
+          const double tmp = a + tp;
+          __syncwarp(); // every lane of the group has read the top entry
+          if(on)
+          {
+            if(c == 0) *top = fma(-tau, tmp, tp);
+            double * upw = Rp + colR(jc) + k + 1;
+            double * low = Vp + offV(jc) - (jc - k);
+            for(int t2 = c; t2 < len; t2 += 4)
+            {
+              double * e = t2 < nup ? upw + t2 : low + t2;
+              *e = fma(-(tau * ess[t2]), tmp, *e);
+            }
+          }
+        }
+      }
+      sync();
+#else
       for(int j = k + 1 + tid; j < q; j += T)
       {
         double * top = Rp + colR(j) + k;
@@ -1587,6 +1638,7 @@ struct GiCta
         }
       }
       sync();
+#endif
     }
 
     // ---- J = J Q, thread = row (rows are independent: no barrier between reflectors)
