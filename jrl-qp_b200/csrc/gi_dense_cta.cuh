@@ -707,6 +707,12 @@ struct GiCta
 #ifndef JRLQP_OPT_RS
 #  define JRLQP_OPT_RS 1
 #endif
+#ifndef JRLQP_CHOL_LPR
+#  define JRLQP_CHOL_LPR 0 // bit 0: one-warp kernel, bit 1: two-warp kernel — last columns of the Cholesky with 2 / 4 lanes per row.
+                           // Measured and rejected (profiles/r5d_ab_*.txt: bit-identical, -1.8 % at n = 50, -17 % at n = 20): at 6 / 16 CTAs
+                           // per SM the narrow kernels are bound by issue slots and the shared-memory pipe, not by the length of a
+                           // column step; the strided 4-lane row reads add bank conflicts and both warps now execute every column.
+#endif
 #ifndef JRLQP_QR4
 #  define JRLQP_QR4 1 // warm start: the Householder QR of the active normals updates its trailing columns with four lanes per column
 #endif
@@ -860,6 +866,64 @@ struct GiCta
   // ------------------------------------------------------------------------------------------
   // init_ (src/GoldfarbIdnaniSolver.cpp:56-82): Cholesky, J = L^-T, x = -G^-1 a, f = a.x/2
   // ------------------------------------------------------------------------------------------
+  // One column of the left-looking Cholesky with G = 2 or 4 lanes per row, for the last T / G columns (rows n - T / G ... n - 1
+  // <-> lane groups 0 ... T / G - 1): lane c of a group runs the chains c, c + G, ... of the canonical dot4 over ITS entries
+  // j = c (mod G) of the row (G = 4: chain c; G = 2: chains 2 c and 2 c + 1), the chains are folded (a0 + a1) + (a2 + a3) by
+  // shuffles (additions commute), lane 0 of the group forms and stores the entry. Same operations in the same order for every
+  // entry as the one-lane-per-row step in init(): same bits; the long inner products of the last columns cost a half / a quarter
+  // and both warps share them. Returns false on a non-positive pivot (uniform).
+  template<int G, bool WRITE_RS = false>
+  __device__ __forceinline__ bool chol_step_split(const int k)
+  {
+    const int g = tid / G, c = tid % G;
+    const int i = n - T / G + g; // (< k: this group has no row in column k)
+    const bool act = i >= k;
+    const double * Li = Jb + (act ? i : k) * ldj;
+    const double * Lk = Jb + k * ldj;
+    double sum;
+    if(G == 4)
+    {
+      double a = 0.0;
+#pragma unroll 2
+      for(int j = c; j < k; j += 4) a = fma(Li[j], Lk[j], a);
+      a = a + __shfl_xor_sync(JRLQP_FULL, a, 1);
+      sum = a + __shfl_xor_sync(JRLQP_FULL, a, 2);
+    }
+    else
+    {
+      double a0 = 0.0, a1 = 0.0;
+      int j = 2 * c;
+#pragma unroll 2
+      for(; j + 1 < k; j += 4)
+      {
+        a0 = fma(Li[j], Lk[j], a0);
+        a1 = fma(Li[j + 1], Lk[j + 1], a1);
+      }
+      if(j < k) a0 = fma(Li[j], Lk[j], a0);
+      const double h = a0 + a1;
+      sum = h + __shfl_xor_sync(JRLQP_FULL, h, 1);
+    }
+    const double v = Li[k] - sum;
+    if(act && i == k && c == 0) scr[0] = v;
+    sync();
+    const double vk = scr[0];
+    if(vk <= 0.0) return false; // Eigen llt: "if (x <= 0) return k" -> NON_POS_HESSIAN (uniform)
+    const double lkk = sqrt(vk);
+    if(act && c == 0)
+    {
+      if(i == k)
+      {
+        Jb[i * ldj + k] = lkk;
+        ldiag[k] = lkk;
+        if(WRITE_RS || !JRLQP_OPT_RS) rs[k] = 1.0 / lkk;
+      }
+      else
+        Jb[i * ldj + k] = v / lkk;
+    }
+    sync();
+    return true;
+  }
+
   __device__ bool init(long long b)
   {
     const double * __restrict__ Gb = P.G + b * P.sG;
@@ -903,8 +967,12 @@ struct GiCta
       constexpr int ACS = 33; // doubles per row of the parked accumulators: [column of the panel][chain] + 1 (odd: conflict-free)
       double * const acs = Rp;
       const bool dmma_on = DMMA && (long long)(32 * W) * ACS <= (long long)n * (n + 1) / 2;
+      // narrow kernels: once no more than T / 2 (T / 4) rows are left below the pivot, a row is given to TWO (FOUR) lanes
+      // (chol_step_split) — the columns with the longest inner products are the ones with the fewest rows
+      constexpr bool LPR = W <= 2 && ((JRLQP_CHOL_LPR >> (W - 1)) & 1) != 0;
+      const int k1 = LPR ? max(0, n - T / 2) : n;
 #pragma unroll 1
-      for(int k = 0; k < n; ++k)
+      for(int k = 0; k < k1; ++k)
       {
         int K0 = 0;
         if(DMMA && dmma_on)
@@ -997,6 +1065,16 @@ struct GiCta
         else if(i > k && i < n)
           Jb[i * ldj + k] = v / lkk;
         sync();
+      }
+      if(LPR)
+      {
+        const int k2 = max(k1, n - T / 4);
+#pragma unroll 1
+        for(int k = k1; k < k2; ++k)
+          if(!chol_step_split<2>(k)) return false;
+#pragma unroll 1
+        for(int k = k2; k < n; ++k)
+          if(!chol_step_split<4>(k)) return false;
       }
 #if JRLQP_OPT_RS
       // reciprocals of the diagonal (for J = L^-T and the two triangular solves): one division per thread,
@@ -1377,8 +1455,10 @@ struct GiCta
     sync();
     {
       const double * Li = Jb + ic * ldj;
+      constexpr bool LPR = W <= 2 && ((JRLQP_CHOL_LPR >> (W - 1)) & 1) != 0; // (as in init())
+      const int k1 = LPR ? max(0, n - T / 2) : n;
 #pragma unroll 1
-      for(int k = 0; k < n; ++k)
+      for(int k = 0; k < k1; ++k)
       {
         double v = 0.0;
         if(32 * warp + 31 >= k)
@@ -1417,6 +1497,20 @@ struct GiCta
         else if(i > k && i < n)
           Jb[i * ldj + k] = v / lkk;
         sync();
+      }
+      if(LPR)
+      {
+        const int k2 = max(k1, n - T / 4);
+        bool pd = true;
+#pragma unroll 1
+        for(int k = k1; k < k2 && pd; ++k) pd = chol_step_split<2, true>(k);
+#pragma unroll 1
+        for(int k = k2; k < n && pd; ++k) pd = chol_step_split<4, true>(k);
+        if(!pd)
+        {
+          if(fc != nullptr && tid == 0) fc[(long long)n * n] = -1.0;
+          return TS_NON_POS_HESSIAN;
+        }
       }
     }
     if(P.L != nullptr)
