@@ -95,6 +95,15 @@ namespace jrlqp
 #ifndef JRLQP_MINB3
 #  define JRLQP_MINB3 1 // resident CTAs per SM the three-warp kernel is compiled for (4: 168 registers, 12 warps per SM)
 #endif
+#ifndef JRLQP_WARM_MINB1
+#  define JRLQP_WARM_MINB1 16 // resident CTAs per SM the one-warp WARM kernel is compiled for: 128 registers, no spill, 16 CTAs per SM
+                              // instead of 225 registers / 8 CTAs: sequences of n = 20 11.86 M -> 13.33 M QP-steps/s (profiles/r5e_*)
+#endif
+#ifndef JRLQP_WARM_MINB2
+#  define JRLQP_WARM_MINB2 6 // the same for the two-warp WARM kernel (n = 33 ... 64): 160 registers instead of 221, no spill; where shared
+                             // memory leaves room (n <= 45) six QPs are resident instead of four: sequences of n = 40 4.30 M -> 5.25 M
+                             // QP-steps/s, n = 50 (four QPs per SM by shared memory either way) 3.05 M -> 3.07 M (profiles/r5f_*)
+#endif
 #ifndef JRLQP_MINB1
 #  define JRLQP_MINB1 16 // resident CTAs per SM the one-warp kernel is compiled for (register cap 65536 / (32 * MINB1))
 #endif
@@ -3267,7 +3276,7 @@ struct GiCta
 // runs 3 QPs per SM where shared memory permits (n <= 77) and is 29 % faster there, 1.5 % slower where it does not
 // (profiles/r4a_ab_w3cap.txt) — the host picks by occupancy (capi.cu).
 template<int W, bool STAGE_C, bool WARM = false, int MINB = 0>
-__global__ void __launch_bounds__(32 * W, (MINB ? MINB : (WARM ? 1 : (W == 1 ? JRLQP_MINB1 : (W == 2 ? 6 : (W == 3 ? JRLQP_MINB3 : 1)))))) gi_dense_cta_kernel(const GiParams p)
+__global__ void __launch_bounds__(32 * W, (MINB ? MINB : (WARM ? (W == 1 ? JRLQP_WARM_MINB1 : (W == 2 ? JRLQP_WARM_MINB2 : 1)) : (W == 1 ? JRLQP_MINB1 : (W == 2 ? 6 : (W == 3 ? JRLQP_MINB3 : 1)))))) gi_dense_cta_kernel(const GiParams p)
 {
   extern __shared__ __align__(16) double smem[];
   GiCta<W, STAGE_C, WARM> cta(p, smem);
