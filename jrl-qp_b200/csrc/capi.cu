@@ -176,6 +176,7 @@ struct jrlqp_solver
   int path_mode = 0; // 0 automatic (n <= 128: shared-memory kernel), 1 shared-memory kernel, 2 global-workspace kernel
   bool large = false;
   int lsmem_bytes[2] = {0, 0}, locc[2] = {0, 0}, lregs[2] = {0, 0}; // [cold, warm]
+  int lring[2] = {0, 0}; // columns per stage of the TMA column ring of the large-n kernel (0: off)
   double * d_work[2] = {nullptr, nullptr};
   double * d_cts = nullptr; // transposed copy of a batch-shared C (large-n kernel)
   int ldcts = 0;
@@ -254,10 +255,37 @@ static int configure_large(jrlqp_solver * s, bool warm)
   }
   const int slots = occ * s->num_sms; // every resident CTA of this kernel, whatever the launch, finds a slice
   occ = std::min(occ, 2);
+  // The streaming passes over J (rotation sweep of an add, z = J2 d2) read their columns through a ring of shared-memory stages
+  // filled by TMA bulk copies (gi_large.cuh: ring_*), when the rows fit two per thread and the stages cost no residency.
+  int smem_total = smem;
+  s->lring[w] = 0;
+  {
+    // Measured (profiles/r5i_*, 32 768 QPs): n = 387 cold 109.4 k -> 132.1 k QP/s (+21 %: 296 workspaces of 1.2 MB do not fit L2, the
+    // sweeps wait on HBM); n = 210 cold -3 % (104 MB of workspaces stay in L2 and the stages take 40 KB of L1 away), warm starts
+    // of the MultiIK fixtures (zero iterations: no sweep at all) -3.5 % / 0 %. Automatic: cold kernel, n >= 256.
+    // JRLQP_LARGE_RING=0: never, =2: whenever it fits.
+    const char * e = getenv("JRLQP_LARGE_RING");
+    const bool want = e ? (e[0] == '2' || (e[0] != '0' && !warm && s->n >= 256)) : (!warm && s->n >= 256);
+    const long long ldl = (s->n + 3) & ~3ll;
+    int rc = (int)std::min<long long>(16, (16384 / (ldl * 8))) & ~3;
+    if(want && s->n <= 2 * kLargeThreads && rc >= 4)
+    {
+      const int with_ring = ((lay.total + 1) & ~1) * 8 + jrlqp::kRingStages * (rc * (int)ldl * 8 + 8);
+      int occ2 = 0;
+      if(with_ring <= s->max_smem_optin && jrlqp::raise_smem_limit(fn, with_ring) == cudaSuccess
+         && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, kLargeThreads, with_ring) == cudaSuccess && occ2 >= occ)
+      {
+        s->lring[w] = rc;
+        smem_total = with_ring;
+      }
+      else
+        cudaGetLastError();
+    }
+  }
   cudaFuncAttributes attr;
   CK(cudaFuncGetAttributes(&attr, fn));
   s->lregs[w] = attr.numRegs;
-  s->lsmem_bytes[w] = smem;
+  s->lsmem_bytes[w] = smem_total;
   s->locc[w] = occ;
   s->work_stride[w] = large_workspace_doubles(s->n, warm);
   s->work_slots[w] = slots;
@@ -752,6 +780,7 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
     p.work_stride = s->work_stride[warm ? 1 : 0];
     p.work_busy = s->d_busy[warm ? 1 : 0];
     p.work_slots = s->work_slots[warm ? 1 : 0];
+    p.ring_cols = s->lring[warm ? 1 : 0];
     if(warm)
       gi_large_kernel<kLargeThreads, true><<<(unsigned)grid, kLargeThreads, s->lsmem_bytes[1], st>>>(p);
     else

@@ -28,6 +28,8 @@
 namespace jrlqp
 {
 
+constexpr int kRingStages = 3; // stages of the TMA-fed column ring (see GiLarge::ring_*)
+
 // Shared-memory carve-up, computed identically on the host (size) and on the device (pointers).
 struct LargeSmem
 {
@@ -99,6 +101,12 @@ struct GiLarge
   double2 * gcs;
   int *alist, *gk, *iscr, *redi;
   signed char *stat, *eqf;
+  // TMA-fed column ring (rcols > 0): kRingStages stages of rcols consecutive columns of the column-major J, filled by
+  // cp.async.bulk copies that complete on one mbarrier per stage; rph holds the phase bit of every stage (uniform)
+  double * ring;
+  unsigned long long * rbar;
+  int rcols;
+  unsigned rph;
   // per-problem views
   const double *Cb, *bl, *bu, *xl, *xu;
   long long ldC;
@@ -141,6 +149,167 @@ struct GiLarge
     Jr = work + (long long)n * ldl;
     Rp = work + 2ll * n * ldl;
     Bw = Rp + ((long long)n * (n + 1) / 2 + 3) / 4 * 4;
+    rcols = p.ring_cols;
+    ring = smem + ((S.total + 1) & ~1);
+    rbar = reinterpret_cast<unsigned long long *>(ring + (long long)kRingStages * rcols * ldl);
+    rph = 0u;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Column ring. The rotation sweep of an add and z = J2 d2 stream J column by column (3 KB per column at n = 387) out of a
+  // per-CTA workspace that lives in L2 / HBM: with plain loads a thread has PF = 4 values in flight and the phases are bound
+  // by the memory latency (profiles/r5h_*: long_scoreboard 55 % of the samples, issue slots 16 % busy). Here ONE thread asks
+  // the TMA unit for the next chunks of rcols whole columns (contiguous in the column-major storage: one bulk copy per
+  // chunk), two chunks ahead of the chunk being used; the threads read their rows from shared memory. Protocol per chunk:
+  // wait on the stage's mbarrier (phase bit in rph) -> use -> block barrier -> the stage is refilled. Writes of J stay plain
+  // global stores; a pass starts with fence.proxy.async.global + block barrier so that the bulk copies (async proxy) see them.
+  // ------------------------------------------------------------------------------------------
+  __device__ __forceinline__ static unsigned saddr(const void * p) { return (unsigned)__cvta_generic_to_shared(p); }
+  __device__ void ring_setup()
+  {
+    if(rcols > 0 && tid == 0)
+    {
+      for(int i = 0; i < kRingStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(rbar + i)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // (one thread) columns [c0, c0 + nc) of J -> stage
+  __device__ __forceinline__ void ring_issue(const int stage, const int c0, const int nc)
+  {
+    const unsigned bar = saddr(rbar + stage);
+    const unsigned bytes = (unsigned)(nc * ldl * 8);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of this stage are done (block barrier)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(ring + (long long)stage * rcols * ldl)),
+                 "l"(Jc + (long long)c0 * ldl), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  __device__ __forceinline__ void ring_wait(const int stage)
+  {
+    const unsigned bar = saddr(rbar + stage), par = (rph >> stage) & 1u;
+    unsigned done;
+    do
+    {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(par) : "memory");
+    } while(!done);
+    rph ^= 1u << stage;
+  }
+  // chunk k of a DESCENDING pass that starts at column n - 1: columns [max(0, hi - rcols + 1), hi], hi = n - 1 - k rcols
+  __device__ __forceinline__ void ring_issue_down(const int k)
+  {
+    const int hi = n - 1 - k * rcols, st = max(0, hi - rcols + 1);
+    ring_issue(k % kRingStages, st, hi - st + 1);
+  }
+  // chunk k of an ASCENDING pass that starts at column c0: columns [c0 + k rcols, min(n, c0 + (k + 1) rcols))
+  __device__ __forceinline__ void ring_issue_up(const int c0, const int k)
+  {
+    const int st = c0 + k * rcols;
+    ring_issue(k % kRingStages, st, min(rcols, n - st));
+  }
+
+  // the rotation sweep of add_constraint() through the ring: rows tid and tid + T of J (n <= 2 T), links n - 2 ... lo
+  __device__ void add_rotations_ring(const int lo)
+  {
+    const int r0 = tid, r1 = tid + T;
+    const bool h0 = r0 < n, h1 = r1 < n;
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    sync();
+    const int nch = (n - lo + rcols - 1) / rcols;
+    if(tid == 0)
+      for(int k = 0; k < kRingStages - 1 && k < nch; ++k) ring_issue_down(k);
+    double y0 = 0.0, y1 = 0.0;
+#pragma unroll 1
+    for(int k = 0; k < nch; ++k)
+    {
+      if(tid == 0 && k + kRingStages - 1 < nch) ring_issue_down(k + kRingStages - 1);
+      const int hi = n - 1 - k * rcols, st = max(0, hi - rcols + 1);
+      ring_wait(k % kRingStages);
+      const double * sb = ring + (long long)(k % kRingStages) * rcols * ldl - (long long)st * ldl; // sb[c * ldl + row] = J(row, c)
+      int i = hi;
+      if(k == 0)
+      {
+        y0 = h0 ? sb[(long long)(n - 1) * ldl + r0] : 0.0;
+        y1 = h1 ? sb[(long long)(n - 1) * ldl + r1] : 0.0;
+        i = n - 2;
+      }
+      const int ilo = max(st, lo);
+#pragma unroll 4
+      for(; i >= ilo; --i)
+      {
+        const double2 cs2 = gcs[i];
+        const double c = cs2.x, sn = cs2.y;
+        const double * col = sb + (long long)i * ldl;
+        double * out = Jc + (long long)(i + 1) * ldl;
+        if(h0)
+        {
+          const double xi = col[r0];
+          out[r0] = fma(c, y0, sn * xi);
+          y0 = fma(c, xi, -(sn * y0));
+        }
+        if(h1)
+        {
+          const double xi = col[r1];
+          out[r1] = fma(c, y1, sn * xi);
+          y1 = fma(c, xi, -(sn * y1));
+        }
+      }
+      if(k + 1 < nch) sync(); // every thread is done with this stage before it is refilled
+    }
+    if(h0) Jc[(long long)lo * ldl + r0] = y0;
+    if(h1) Jc[(long long)lo * ldl + r1] = y1;
+  }
+
+  // z = J2 d2 through the ring (rows tid and tid + T): the first chunks were requested by compute_step() before d was formed
+  __device__ void z_ring()
+  {
+    const int r0 = tid, r1 = tid + T;
+    const bool h0 = r0 < n, h1 = r1 < n;
+    const int nch = (n - q + rcols - 1) / rcols;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll 1
+    for(int k = 0; k < nch; ++k)
+    {
+      if(tid == 0 && k + kRingStages - 1 < nch) ring_issue_up(q, k + kRingStages - 1);
+      const int st = q + k * rcols, en = min(n, st + rcols);
+      ring_wait(k % kRingStages);
+      const double * sb = ring + (long long)(k % kRingStages) * rcols * ldl - (long long)st * ldl;
+      const double * p0 = sb + (h0 ? r0 : 0);
+      const double * p1 = sb + (h1 ? r1 : 0);
+      int c = st;
+#pragma unroll 2
+      for(; c + 3 < en; c += 4)
+      {
+        const double d0 = ds[c], d1 = ds[c + 1], d2 = ds[c + 2], d3 = ds[c + 3];
+        a0 = fma(p0[(long long)c * ldl], d0, a0);
+        a1 = fma(p0[(long long)(c + 1) * ldl], d1, a1);
+        a2 = fma(p0[(long long)(c + 2) * ldl], d2, a2);
+        a3 = fma(p0[(long long)(c + 3) * ldl], d3, a3);
+        b0 = fma(p1[(long long)c * ldl], d0, b0);
+        b1 = fma(p1[(long long)(c + 1) * ldl], d1, b1);
+        b2 = fma(p1[(long long)(c + 2) * ldl], d2, b2);
+        b3 = fma(p1[(long long)(c + 3) * ldl], d3, b3);
+      }
+      // (only the last chunk has a tail: the chunks before it hold a multiple of four columns)
+      if(c < en)
+      {
+        a0 = fma(p0[(long long)c * ldl], ds[c], a0);
+        b0 = fma(p1[(long long)c * ldl], ds[c], b0);
+      }
+      if(c + 1 < en)
+      {
+        a1 = fma(p0[(long long)(c + 1) * ldl], ds[c + 1], a1);
+        b1 = fma(p1[(long long)(c + 1) * ldl], ds[c + 1], b1);
+      }
+      if(c + 2 < en)
+      {
+        a2 = fma(p0[(long long)(c + 2) * ldl], ds[c + 2], a2);
+        b2 = fma(p1[(long long)(c + 2) * ldl], ds[c + 2], b2);
+      }
+      if(k + 1 < nch) sync();
+    }
+    if(h0) zs[r0] = (a0 + a1) + (a2 + a3);
+    if(h1) zs[r1] = (b0 + b1) + (b2 + b3);
   }
 
   __device__ __forceinline__ static long long colR(int k) { return ((long long)k * (k + 1)) >> 1; }
@@ -633,7 +802,14 @@ struct GiLarge
     const bool general = sc.st < ST_LOWER_BOUND;
     if(general)
       for(int i = tid; i < n; i += T) cv[i] = Cb[(long long)sc.p * ldC + i];
+    if(rcols > 0) asm volatile("fence.proxy.async.global;" ::: "memory"); // (the last writes of J, before the barrier below)
     sync();
+    if(rcols > 0 && tid == 0)
+    {
+      // the first chunks of z = J2 d2 travel while d is formed
+      const int nch = (n - q + rcols - 1) / rcols;
+      for(int k = 0; k < kRingStages - 1 && k < nch; ++k) ring_issue_up(q, k);
+    }
     if(general)
     {
       // d, thread = column j of the column-major J: 32-byte vector loads down the column
@@ -671,6 +847,9 @@ struct GiLarge
     }
     sync();
     // z, thread = row i: z[i] = dot4_{j=q..n-1}(J(i,j), d[j]), accumulator (j-q)&3 — coalesced
+    if(rcols > 0)
+      z_ring();
+    else
     for(int i = tid; i < n; i += T)
     {
       const double * Ji = Jc + i;
@@ -819,7 +998,9 @@ struct GiLarge
   {
     q += 1;
     const int lo = q - 1;
-    if(lo <= n - 2)
+    if(lo <= n - 2 && rcols > 0)
+      add_rotations_ring(lo);
+    else if(lo <= n - 2)
     {
       for(int row = tid; row < n; row += T)
       {
@@ -1143,6 +1324,7 @@ __global__ void __launch_bounds__(T, 2) gi_large_kernel(const GiParams p)
   __syncthreads();
   const int slot = slot_s;
   GiLarge<T, WARM> cta(p, smem, p.work + (long long)slot * p.work_stride);
+  cta.ring_setup();
   for(;;)
   {
     __syncthreads();

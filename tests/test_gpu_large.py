@@ -279,3 +279,38 @@ def test_concurrent_launches_on_two_streams_do_not_share_a_workspace():
     torch.cuda.synchronize()
     for sl, x, it in outs:
         assert np.array_equal(x.cpu().numpy(), ref["x"][sl]) and np.array_equal(it.cpu().numpy(), ref["iterations"][sl])
+
+
+# ---------------------------------------------------------------------------------------------
+# TMA column ring (gi_large.cuh ring_*): the rotation sweep and z = J2 d2 read J through bulk copies
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [20, 50, 131, 212, 300, 512])
+@pytest.mark.parametrize("warm", [False, True])
+def test_tma_column_ring_is_invisible(n, warm):
+    """Same bits with the ring forced on (JRLQP_LARGE_RING=2: every n <= 512 that fits, cold and warm kernels) and off
+    (=0), and equal to the oracle: row counts below / at / above one and two rows per thread, column counts that are not
+    a multiple of the stage width, sweeps shorter than one stage (many pre-activated equalities)."""
+    ne = n // 3
+    ch = P.ProblemCharacteristics(n, ne, n - ne, nStrongActIneq=max(1, n // 6), bounds=True, nStrongActBounds=n // 8,
+                                  doubleSidedIneq=True)
+    pb = P.random_problems(ch, 24 if n > 256 else 96, seed=700 + n)
+    old = os.environ.get("JRLQP_LARGE_RING")
+    out = {}
+    try:
+        for ring in ("2", "0"):
+            os.environ["JRLQP_LARGE_RING"] = ring
+            if warm:
+                cold = _oracle(pb)
+                guess = np.roll(cold["active_set"], 1, axis=0)  # a neighbour's active set: a few iterations to repair it
+                out[ring] = _gpu_warm(pb, guess)
+            else:
+                out[ring] = _gpu(pb)
+    finally:
+        if old is None:
+            os.environ.pop("JRLQP_LARGE_RING")
+        else:
+            os.environ["JRLQP_LARGE_RING"] = old
+    for k in ("x", "u", "f", "iterations", "status", "active_set"):
+        assert np.array_equal(out["2"][k], out["0"][k]), k
+    ref = _oracle_warm(pb, np.roll(_oracle(pb)["active_set"], 1, axis=0)) if warm else _oracle(pb)
+    assert_parity(out["2"], ref)
