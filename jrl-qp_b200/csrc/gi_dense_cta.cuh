@@ -306,18 +306,38 @@ __device__ __forceinline__ double dot4_row(const double * __restrict__ ci, const
 __device__ __forceinline__ long long ct_offset(int c, int n) { return ((long long)(c >> 7) * n) * JRLQP_CT_LD + (c & (JRLQP_CT_LD - 1)); }
 __host__ __device__ inline long long ct_doubles(int n, int mc) { return (long long)((mc + JRLQP_CT_LD - 1) / JRLQP_CT_LD) * n * JRLQP_CT_LD; }
 
-template<int CH>
+// EVL: the loads carry an L2 evict_last policy (createpolicy + ld.global.cg.L2::cache_hint). For the large-n kernel, whose
+// transposed C is ONE 5 MB copy shared by every CTA while 296 workspaces of 1.2 MB stream through L2: config C +7 %
+// (profiles/r5l_*); the per-CTA copies of the four-warp kernel lose 3 % with it, hence a template parameter.
+#ifndef JRLQP_CT_EVICT_LAST
+#  define JRLQP_CT_EVICT_LAST 1
+#endif
+template<bool EVL>
+__device__ __forceinline__ double ct_load(const double * p, const unsigned long long pol)
+{
+  if(EVL)
+  {
+    double v;
+    asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+  }
+  return __ldcg(p);
+}
+
+template<int CH, bool EVL = false>
 __device__ __forceinline__ double dot4_col(const double * ci, const double * xs, int n, const bool act = true)
 {
   constexpr int ld = JRLQP_CT_LD;
   double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   int k = 0;
+  unsigned long long pol = 0ull;
+  if(EVL) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 #pragma unroll 1
   for(; k + CH - 1 < n; k += CH)
   {
     double v[CH];
 #pragma unroll
-    for(int u = 0; u < CH; ++u) v[u] = act ? __ldcg(ci + (k + u) * ld) : 0.0;
+    for(int u = 0; u < CH; ++u) v[u] = act ? ct_load<EVL>(ci + (k + u) * ld, pol) : 0.0;
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
     {
@@ -330,7 +350,7 @@ __device__ __forceinline__ double dot4_col(const double * ci, const double * xs,
   {
     double v[CH];
 #pragma unroll
-    for(int u = 0; u < CH; ++u) v[u] = (k + u < n && act) ? __ldcg(ci + (k + u) * ld) : 0.0;
+    for(int u = 0; u < CH; ++u) v[u] = (k + u < n && act) ? ct_load<EVL>(ci + (k + u) * ld, pol) : 0.0;
 #pragma unroll
     for(int u = 0; u < CH / 4; ++u)
     {
