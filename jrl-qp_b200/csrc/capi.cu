@@ -177,6 +177,7 @@ struct jrlqp_solver
   bool large = false;
   int lsmem_bytes[2] = {0, 0}, locc[2] = {0, 0}, lregs[2] = {0, 0}; // [cold, warm]
   int lring[2] = {0, 0}; // columns per stage of the TMA column ring of the large-n kernel (0: off)
+  int lslab = 0; // rows per slab of J = J Q in the warm large-n kernel (0: off)
   double * d_work[2] = {nullptr, nullptr};
   double * d_cts = nullptr; // transposed copy of a batch-shared C (large-n kernel)
   int ldcts = 0;
@@ -270,7 +271,7 @@ static int configure_large(jrlqp_solver * s, bool warm)
     int rc = (int)std::min<long long>(16, (16384 / (ldl * 8))) & ~3;
     if(want && s->n <= 2 * kLargeThreads && rc >= 4)
     {
-      const int with_ring = ((lay.total + 1) & ~1) * 8 + jrlqp::kRingStages * (rc * (int)ldl * 8 + 8);
+      const int with_ring = ((lay.total + 1) & ~1) * 8 + (int)jrlqp::large_ring_doubles(s->n, rc) * 8;
       int occ2 = 0;
       if(with_ring <= s->max_smem_optin && jrlqp::raise_smem_limit(fn, with_ring) == cudaSuccess
          && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, kLargeThreads, with_ring) == cudaSuccess && occ2 >= occ)
@@ -280,6 +281,32 @@ static int configure_large(jrlqp_solver * s, bool warm)
       }
       else
         cudaGetLastError();
+    }
+  }
+  if(warm)
+  {
+    // J = J Q of the warm start on slabs of 16 / 8 rows of J in shared memory (gi_large_warm.inl: warm_JQ_slab), when they cost
+    // no residency. JRLQP_LARGE_SLAB=0: off (the thread = row version on the global workspace).
+    s->lslab = 0;
+    const char * e = getenv("JRLQP_LARGE_SLAB");
+    if(!e || e[0] != '0')
+    {
+      const int base = smem_total == smem ? ((lay.total + 1) & ~1) * 8 : smem_total;
+      for(int R : {16, 8})
+      {
+        const long long bytes = jrlqp::large_slab_doubles(s->n, R) * 8;
+        if(bytes > 36 * 1024) continue;
+        const int tot = base + (int)bytes;
+        int occ2 = 0;
+        if(tot <= s->max_smem_optin && jrlqp::raise_smem_limit(fn, tot) == cudaSuccess
+           && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, kLargeThreads, tot) == cudaSuccess && occ2 >= occ)
+        {
+          s->lslab = R;
+          smem_total = tot;
+          break;
+        }
+        cudaGetLastError();
+      }
     }
   }
   cudaFuncAttributes attr;
@@ -781,6 +808,7 @@ static int launch(jrlqp_solver * s, const jrlqp_problem * pb, const jrlqp_result
     p.work_busy = s->d_busy[warm ? 1 : 0];
     p.work_slots = s->work_slots[warm ? 1 : 0];
     p.ring_cols = s->lring[warm ? 1 : 0];
+    p.slab_rows = warm ? s->lslab : 0;
     if(warm)
       gi_large_kernel<kLargeThreads, true><<<(unsigned)grid, kLargeThreads, s->lsmem_bytes[1], st>>>(p);
     else

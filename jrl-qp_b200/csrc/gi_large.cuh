@@ -85,6 +85,17 @@ struct LargeSmem
   }
 };
 
+// shared memory behind the LargeSmem carve-up (doubles): the column ring with its barriers, then the slab of the warm start
+__host__ __device__ inline long long large_ring_doubles(int n, int ring_cols)
+{
+  const long long ldl = (n + 3) & ~3;
+  return ring_cols > 0 ? (long long)kRingStages * ring_cols * ldl + ((kRingStages + 1) & ~1) : 0;
+}
+__host__ __device__ inline long long large_slab_doubles(int n, int slab_rows)
+{
+  return slab_rows > 0 ? (long long)n * slab_rows + 2ll * ((n + 1) & ~1) + 16 : 0;
+}
+
 __host__ __device__ inline long long large_workspace_doubles(int n, bool warm)
 {
   const long long ldl = (n + 3) & ~3;
@@ -116,6 +127,9 @@ struct GiLarge
   unsigned long long * rbar;
   int rcols;
   unsigned rph;
+  // warm start: slab of srows rows of J (all columns) for J = J Q, two buffers for the essential part of a reflector, tau tmp per row
+  double * slab;
+  int srows;
   // per-problem views
   const double *Cb, *bl, *bu, *xl, *xu;
   long long ldC;
@@ -162,6 +176,8 @@ struct GiLarge
     ring = smem + ((S.total + 1) & ~1);
     rbar = reinterpret_cast<unsigned long long *>(ring + (long long)kRingStages * rcols * ldl);
     rph = 0u;
+    slab = ring + large_ring_doubles(n, rcols);
+    srows = p.slab_rows;
   }
 
   // ------------------------------------------------------------------------------------------

@@ -259,9 +259,141 @@ __device__ void warm_qr()
   sync();
 }
 
+// J = J Q with the rows of J taken through shared memory, R = srows (8 or 16) at a time. The reflectors act on the rows of J
+// independently, and a row needs ALL its entries twice per reflector (inner product, then update): with thread = row on the
+// column-major workspace (warm_JQ below) every reflector streams J twice from L2 / HBM with a few values per thread in flight
+// — 60 % of a warm-started n = 387 solve (profiles/r5o_*: long_scoreboard, issue slots 8 % busy). Here a slab of R rows (all
+// columns: R n doubles, 25 KB at n = 387) is loaded once, every reflector is applied to it on chip, and it is stored once.
+// Inner product of a row: four lanes, lane c runs chain c of the canonical dot4 (entries t = c, c + 4, ... ascending), the
+// chains are folded (a0 + a1) + (a2 + a3) by two shuffles; update: all threads, one entry each. Same operations per entry in
+// the same order as warm_JQ: same bits. The essential part of the next reflector is staged by the warps that have no inner
+// product to run.
+__device__ void warm_JQ_slab()
+{
+  const int R = srows, rs = R == 16 ? 4 : 3;
+  double * S = slab; // S[c * R + r] = J(r0 + r, c)
+  const int ne = (n + 1) & ~1;
+  double * E0 = slab + (long long)n * R; // two buffers for ess_k
+  double * TT = E0 + 2 * ne; // tau * tmp of every row of the slab
+  const int ndot = 4 * R; // threads of the inner products (whole warps: R = 8 / 16)
+  for(int r0 = 0; r0 < n; r0 += R)
+  {
+    const int nr = min(R, n - r0);
+    // ---- load the slab (8 consecutive threads read 64 contiguous bytes of a column), four values in flight per thread
+    {
+      const int tot = n << rs;
+      for(int e0 = tid; e0 < tot; e0 += 4 * T)
+      {
+        double v[4];
+#pragma unroll
+        for(int u = 0; u < 4; ++u)
+        {
+          const int e = e0 + u * T;
+          const int c = e >> rs, r = e & (R - 1);
+          v[u] = (e < tot && r < nr) ? Jc[(long long)c * ldl + r0 + r] : 0.0;
+        }
+#pragma unroll
+        for(int u = 0; u < 4; ++u)
+          if(e0 + u * T < tot) S[e0 + u * T] = v[u];
+      }
+    }
+    // first reflector with something to do: stage its essential part
+    int k = 0;
+    while(k < q && !(n - k - 1 == 0 || hco[k] != 0.0)) ++k;
+    int buf = 0;
+    if(k < q)
+    {
+      const int len = n - k - 1;
+      const double * ess = Bw + (long long)k * ldl + k + 1;
+      for(int t = tid; t < len; t += T) E0[t] = ess[t];
+    }
+    sync();
+#pragma unroll 1
+    while(k < q)
+    {
+      const int len = n - k - 1;
+      const double tau = hco[k];
+      int kn = k + 1; // the next reflector with something to do
+      while(kn < q && !(n - kn - 1 == 0 || hco[kn] != 0.0)) ++kn;
+      const double * E = E0 + buf * ne;
+      if(len == 0)
+      {
+        if(tid < nr) S[(k << rs) + tid] = S[(k << rs) + tid] * (1.0 - tau);
+      }
+      else
+      {
+        if(tid < ndot)
+        {
+          const int r = tid >> 2, c = tid & 3;
+          const double * Sr = S + ((long long)(k + 1) << rs) + r;
+          double a = 0.0;
+#pragma unroll 4
+          for(int t = c; t < len; t += 4) a = fma(Sr[t << rs], E[t], a);
+          a = a + __shfl_xor_sync(JRLQP_FULL, a, 1);
+          a = a + __shfl_xor_sync(JRLQP_FULL, a, 2);
+          const double top = S[(k << rs) + r];
+          const double tmp = a + top;
+          __syncwarp();
+          if(c == 0)
+          {
+            S[(k << rs) + r] = fma(-tau, tmp, top);
+            TT[r] = tau * tmp;
+          }
+        }
+        else if(kn < q)
+        {
+          // the other warps stage ess of the next reflector meanwhile
+          const int lenn = n - kn - 1;
+          const double * essn = Bw + (long long)kn * ldl + kn + 1;
+          double * En = E0 + (buf ^ 1) * ne;
+          for(int t = tid - ndot; t < lenn; t += T - ndot) En[t] = essn[t];
+        }
+        sync();
+        // update: entry (t2, r) <- fma(-tt_r, ess[t2], entry)
+        {
+          const int tot = len << rs;
+          double * Su = S + ((long long)(k + 1) << rs);
+          for(int e = tid; e < tot; e += T)
+          {
+            const int t2 = e >> rs, r = e & (R - 1);
+            Su[e] = fma(-TT[r], E[t2], Su[e]);
+          }
+        }
+      }
+      sync();
+      if(len == 0 && kn < q)
+      {
+        // (k = n - 1 is the last reflector there can be: nothing follows; kept for completeness)
+        const int lenn = n - kn - 1;
+        const double * essn = Bw + (long long)kn * ldl + kn + 1;
+        double * En = E0 + (buf ^ 1) * ne;
+        for(int t = tid; t < lenn; t += T) En[t] = essn[t];
+        sync();
+      }
+      buf ^= 1;
+      k = kn;
+    }
+    // ---- store the slab
+    {
+      const int tot = n << rs;
+      for(int e = tid; e < tot; e += T)
+      {
+        const int c = e >> rs, r = e & (R - 1);
+        if(r < nr) Jc[(long long)c * ldl + r0 + r] = S[e];
+      }
+    }
+    sync();
+  }
+}
+
 // J = J Q (HouseholderSequence::applyThisOnTheRight), thread = row of the column-major J
 __device__ void warm_JQ()
 {
+  if(srows > 0)
+  {
+    warm_JQ_slab();
+    return;
+  }
   for(int row = tid; row < n; row += T)
   {
     double * Ji = Jc + row;

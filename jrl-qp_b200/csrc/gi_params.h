@@ -71,6 +71,7 @@ struct GiParams
   int * work_busy; // one flag per slice: a CTA claims a free slice when it starts and releases it when it exits
   int work_slots;
   int ring_cols; // large-n kernel: columns of J per stage of the TMA-fed column ring (gi_large.cuh: ring_*), 0 = off
+  int slab_rows; // large-n WARM kernel: rows of J per shared-memory slab of J = J Q (gi_large_warm.inl: warm_JQ_slab), 8 / 16, 0 = off
   // factor of a batch-shared G (sG == 0), large-n kernel: computed once by gi_large_prefactor_kernel, copied by the CTAs.
   // Layout (doubles, ldl = n rounded up to 4): [0, n ldl) J = L^-T column-major (upper triangle, rest 0),
   // [n ldl, 2 n ldl) scratch of the prefactor kernel, [2 n ldl, 3 n ldl) L column-major, then diag(L) [nv], 1 / diag(L) [nv]

@@ -295,10 +295,12 @@ def test_tma_column_ring_is_invisible(n, warm):
                                   doubleSidedIneq=True)
     pb = P.random_problems(ch, 24 if n > 256 else 96, seed=700 + n)
     old = os.environ.get("JRLQP_LARGE_RING")
+    old_slab = os.environ.get("JRLQP_LARGE_SLAB")
     out = {}
     try:
         for ring in ("2", "0"):
             os.environ["JRLQP_LARGE_RING"] = ring
+            os.environ["JRLQP_LARGE_SLAB"] = "1" if ring == "2" else "0"  # (warm start: J = J Q on shared-memory slabs, on / off)
             if warm:
                 cold = _oracle(pb)
                 guess = np.roll(cold["active_set"], 1, axis=0)  # a neighbour's active set: a few iterations to repair it
@@ -306,10 +308,11 @@ def test_tma_column_ring_is_invisible(n, warm):
             else:
                 out[ring] = _gpu(pb)
     finally:
-        if old is None:
-            os.environ.pop("JRLQP_LARGE_RING")
-        else:
-            os.environ["JRLQP_LARGE_RING"] = old
+        for name, val in (("JRLQP_LARGE_RING", old), ("JRLQP_LARGE_SLAB", old_slab)):
+            if val is None:
+                os.environ.pop(name)
+            else:
+                os.environ[name] = val
     for k in ("x", "u", "f", "iterations", "status", "active_set"):
         assert np.array_equal(out["2"][k], out["0"][k]), k
     ref = _oracle_warm(pb, np.roll(_oracle(pb)["active_set"], 1, axis=0)) if warm else _oracle(pb)
