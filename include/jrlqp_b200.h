@@ -252,6 +252,10 @@ int jrlqp_selftest_arith(int32_t device, int64_t samples, uint64_t seed, int32_t
  *                       reference benchmark
  *   status_worst        [batch] (nullable) worst TerminationStatus over the steps
  * res->active_set is required when warm != 0 (it carries the active set from step to step).
+ * G does not change along a sequence: with warm != 0 and n <= 128 the handle keeps the factor step 0 leaves (L, L^-T and
+ * the diagonal: (n n + 2 n) doubles per instance, device memory owned by the handle and sized by the largest call) and
+ * the later steps re-read it instead of factorising again — same operands, same bits; JRLQP_SEQ_FCACHE=0 in the
+ * environment (read by jrlqp_create) turns it off. The reference refactorises on every call (its solve() overwrites G).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct jrlqp_sequence
 {
