@@ -31,6 +31,9 @@ namespace jrlqp
 #ifndef JRLQP_LARGE_D_PREFETCH
 #  define JRLQP_LARGE_D_PREFETCH 0 // d = J^T n+: L2 prefetch distance down a thread's own column, in doubles. Measured: 128 -> -1 %, 256 -> -3 % on config C (profiles/r5k_*): off
 #endif
+#ifndef JRLQP_WARMB_FAST
+#  define JRLQP_WARMB_FAST 1 // warm start, B = L^-1 N: entries of L loaded one group of rows ahead, quotients from the stored reciprocals (proven)
+#endif
 #ifndef JRLQP_RING_STAGES
 #  define JRLQP_RING_STAGES 3
 #endif

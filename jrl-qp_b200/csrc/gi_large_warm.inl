@@ -141,6 +141,77 @@ __device__ void warm_B(long long b, const double * __restrict__ Lw)
         a3 = fma(l3, b23.y, a3);
       }
       const int nblk = min(32, n - r0);
+#if JRLQP_WARMB_FAST
+      // The 32 rows of the block are finished one after the other: what is serial is one quotient, one shuffle and one fma per
+      // row. The entries of L a group of four rows needs do not depend on the chain: they are loaded one group AHEAD (one L2
+      // round trip per four rows off the serial path instead of one per row on it), and the quotient comes from the stored
+      // reciprocal of the diagonal with its proof of correct rounding (fp64_exact.cuh; the stock division when it declines).
+      const double rlr = rinv[rc];
+      double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+      if(r < n)
+      {
+        if(lane > 0) l0 = Lr[(long long)r0 * ldl];
+        if(lane > 1 && 1 < nblk) l1 = Lr[(long long)(r0 + 1) * ldl];
+        if(lane > 2 && 2 < nblk) l2 = Lr[(long long)(r0 + 2) * ldl];
+        if(lane > 3 && 3 < nblk) l3 = Lr[(long long)(r0 + 3) * ldl];
+      }
+#pragma unroll 1
+      for(int jj = 0; jj < nblk; jj += 4)
+      {
+        double m0 = 0, m1 = 0, m2 = 0, m3 = 0; // the next group
+        if(r < n && jj + 4 < nblk)
+        {
+          if(lane > jj + 4) m0 = Lr[(long long)(r0 + jj + 4) * ldl];
+          if(lane > jj + 5 && jj + 5 < nblk) m1 = Lr[(long long)(r0 + jj + 5) * ldl];
+          if(lane > jj + 6 && jj + 6 < nblk) m2 = Lr[(long long)(r0 + jj + 6) * ldl];
+          if(lane > jj + 7 && jj + 7 < nblk) m3 = Lr[(long long)(r0 + jj + 7) * ldl];
+        }
+        // r0 is a multiple of 4: column r0 + jj + u feeds chain u
+        {
+          const double num = nr - ((a0 + a1) + (a2 + a3));
+          bool okd;
+          double val = div_rcp(num, lrr, rlr, okd);
+          if(!okd) val = num / lrr;
+          const double bj = __shfl_sync(JRLQP_FULL, val, jj);
+          if(lane == jj) Bk[r] = val;
+          if(lane > jj && r < n) a0 = fma(l0, bj, a0);
+        }
+        if(jj + 1 < nblk)
+        {
+          const double num = nr - ((a0 + a1) + (a2 + a3));
+          bool okd;
+          double val = div_rcp(num, lrr, rlr, okd);
+          if(!okd) val = num / lrr;
+          const double bj = __shfl_sync(JRLQP_FULL, val, jj + 1);
+          if(lane == jj + 1) Bk[r] = val;
+          if(lane > jj + 1 && r < n) a1 = fma(l1, bj, a1);
+        }
+        if(jj + 2 < nblk)
+        {
+          const double num = nr - ((a0 + a1) + (a2 + a3));
+          bool okd;
+          double val = div_rcp(num, lrr, rlr, okd);
+          if(!okd) val = num / lrr;
+          const double bj = __shfl_sync(JRLQP_FULL, val, jj + 2);
+          if(lane == jj + 2) Bk[r] = val;
+          if(lane > jj + 2 && r < n) a2 = fma(l2, bj, a2);
+        }
+        if(jj + 3 < nblk)
+        {
+          const double num = nr - ((a0 + a1) + (a2 + a3));
+          bool okd;
+          double val = div_rcp(num, lrr, rlr, okd);
+          if(!okd) val = num / lrr;
+          const double bj = __shfl_sync(JRLQP_FULL, val, jj + 3);
+          if(lane == jj + 3) Bk[r] = val;
+          if(lane > jj + 3 && r < n) a3 = fma(l3, bj, a3);
+        }
+        l0 = m0;
+        l1 = m1;
+        l2 = m2;
+        l3 = m3;
+      }
+#else
 #pragma unroll 1
       for(int jj = 0; jj < nblk; jj += 4)
       {
@@ -173,6 +244,7 @@ __device__ void warm_B(long long b, const double * __restrict__ Lw)
           if(lane > jj + 3 && r < n) a3 = fma(Lr[(long long)(r0 + jj + 3) * ldl], bj, a3);
         }
       }
+#endif
     }
   }
 }
