@@ -31,6 +31,9 @@ namespace jrlqp
 #ifndef JRLQP_LARGE_D_PREFETCH
 #  define JRLQP_LARGE_D_PREFETCH 0 // d = J^T n+: L2 prefetch distance down a thread's own column, in doubles. Measured: 128 -> -1 %, 256 -> -3 % on config C (profiles/r5k_*): off
 #endif
+#ifndef JRLQP_LARGE_D_UNROLL
+#  define JRLQP_LARGE_D_UNROLL 4 // d = J^T n+: iterations (32 bytes of a thread's column each) in flight; 2 -> 4: config C cold +3.9 % (profiles/r5v_ab.txt), no spill
+#endif
 #ifndef JRLQP_WARMB_FAST
 #  define JRLQP_WARMB_FAST 1 // warm start, B = L^-1 N: entries of L loaded one group of rows ahead, quotients from the stored reciprocals (proven)
 #endif
@@ -850,6 +853,7 @@ struct GiLarge
     if(general)
     {
       // d, thread = column j of the column-major J: 32-byte vector loads down the column
+      constexpr int DU = JRLQP_LARGE_D_UNROLL;
       for(int j = tid; j < n; j += T)
       {
         const double * Jj = Jc + (long long)j * ldl;
@@ -860,7 +864,7 @@ struct GiLarge
         // (the 296 workspaces of 1.2 MB do not fit L2: without the hint every line is an HBM round trip on the dependent path)
         for(int o = 0; o < JRLQP_LARGE_D_PREFETCH && o < n; o += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(Jj + o));
 #endif
-#pragma unroll 2
+#pragma unroll DU
         for(; i + 3 < n; i += 4)
         {
 #if JRLQP_LARGE_D_PREFETCH
